@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py - the cost-volume hot path on B200, measured the way BASELINE.json asks.
+
+One "step" = one pass of the whole path over one batch of synthetic stereo pairs:
+    stereo correlation (TF32 tcgen05) + mono correlation (x1.73) + truncation product + two
+    avg-pooled pyramids + 32 GRU iterations x (stereo lookup + mono lookup).
+Default workload = BASELINE.json configs[1]: KITTI-size 375x1242 pairs (padded to 384x1248, quarter
+resolution 96x312), batch 8 per GPU, C=256, 4 levels, radius 4, 32 iterations.
+
+    python bench.py                      # N=1, K=10, W=3
+    python bench.py --impl reference     # the reference's CPU op sequence (oracle port) on host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM);
+`e2e` goes through the public CorrBlockB200 API from pinned HOST buffers with the H2D / D2H copies
+inside the timed region.  `roofline` is for the dominant kernel (the lookup), timed live with CUDA
+events inside the timed region; `cpu_baseline` is the oracle port timed on this box's host cores on
+a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B per GPU, C, H/4, W/4)
+    "c1_384x512_b1": (1, 256, 96, 128),
+    "c2_kitti_375x1242_b8": (8, 256, 96, 312),
+    "c3_sceneflow_540x960_b8": (8, 256, 136, 240),
+    "c4_middlebury_tile_1120x672_b1": (1, 256, 280, 168),
+    "c5_sweep_c256_w768_b1": (1, 256, 96, 768),
+}
+DEFAULT_WORKLOAD = "c2_kitti_375x1242_b8"
+ITERS, LEVELS, RADIUS = 32, 4, 4
+METRIC = "stereo pairs/sec @375x1242, 32 iters (cost-volume path: corr + pyramid + lookup)"
+UNIT = "pairs/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic inputs
+# ------------------------------------------------------------------------------------------
+
+def make_inputs(b, c, h, w, device, seed=0, pinned=False):
+    g = torch.Generator().manual_seed(seed)
+    fl = torch.randn(b, c, h, w, generator=g)
+    fr = torch.randn(b, c, h, w, generator=g)
+    nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w, generator=g), dim=1)
+    nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w, generator=g), dim=1)
+    x = torch.arange(w, dtype=torch.float32).view(1, 1, 1, w).expand(b, 1, h, w)
+    y = torch.arange(h, dtype=torch.float32).view(1, 1, h, 1).expand(b, 1, h, w)
+    coords0 = torch.cat([x - torch.rand(b, 1, h, w, generator=g) * (w / 4), y], 1).contiguous()
+    # per-iteration update the GRU would produce: a small sub-pixel drift, zero in y
+    delta = torch.cat([(torch.rand(b, 1, h, w, generator=g) - 0.5) * 0.5, torch.zeros(b, 1, h, w)], 1).contiguous()
+    tdisp = (torch.rand(b, 1, h, w, generator=g) * (w / 4)).contiguous()
+    tconf = torch.rand(b, 1, h, w, generator=g).contiguous()
+    host = dict(fl=fl, fr=fr, nl=nl, nr=nr, coords0=coords0, delta=delta, tdisp=tdisp, tconf=tconf)
+    if pinned:
+        host = {k: v.pin_memory() for k, v in host.items()}
+    if device is None:
+        return host, None
+    dev = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+    return host, dev
+
+
+def path_bytes(b, c, h, w):
+    """Algorithmic bytes of one step (SURVEY.md 8d / DESIGN.md)."""
+    p = b * h * w
+    stereo = 2 * b * c * h * w * 4 + p * w * 4 + 0.875 * p * w * 4
+    mono = 2 * b * 3 * h * w * 4 + p * w * 4 + 0.875 * p * w * 4
+    lookups = ITERS * 612 * p
+    return stereo + mono + lookups
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, 200 ms) - evidence that the timed region was not throttled
+# ------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# the path on the GPU, through the public API
+# ------------------------------------------------------------------------------------------
+
+class GpuPath:
+    def __init__(self, sa, d, variant):
+        self.sa, self.d, self.variant = sa, d, variant
+        self.ev = None  # (start, end) events around the lookup loop of the current step
+        self.launches = 0
+
+    def build(self):
+        sa, d = self.sa, self.d
+        B = sa.CorrBlockB200
+        if self.variant == "fused":
+            vs = B.corr(d["fl"], d["fr"])
+            vm = B.mono_corr(d["nl"], d["nr"])
+            fs = B(vs, radius=RADIUS, num_levels=LEVELS, truncate=(d["tdisp"], d["tconf"], 0.9))
+            fm = B(vm, radius=RADIUS, num_levels=LEVELS)
+            self.launches += 4
+        else:  # strict reference protocol, op for op (stereoanywhere.py:135-136, 203, 253-259)
+            vs = B.corr(d["fl"], d["fr"]).squeeze(3).unsqueeze(1)
+            vm = 1.73 * B.corr(d["nl"], d["nr"]).squeeze(3).unsqueeze(1)
+            t = sa.truncation_mask(d["tdisp"], d["tconf"], 0.9)
+            fs = B((t * vs).squeeze(1).unsqueeze(3), radius=RADIUS, num_levels=LEVELS)
+            fm = B(vm.squeeze(1).unsqueeze(3), radius=RADIUS, num_levels=LEVELS)
+            self.launches += 5
+        return fs, fm
+
+    def lookups(self, fs, fm, coords, delta, timed_events=None):
+        B = self.sa.CorrBlockB200
+        if timed_events is not None:
+            timed_events[0].record()
+        s = m = None
+        for _ in range(ITERS):
+            if self.variant == "fused":
+                s, m = B.lookup_pair(fs, fm, coords)
+                self.launches += 1
+            else:
+                s, m = fs(coords), fm(coords)
+                self.launches += 2
+            coords = coords + delta  # stands in for the GRU's coords1 += delta_flow (stereoanywhere.py:280)
+        if timed_events is not None:
+            timed_events[1].record()
+        return s, m, coords
+
+    def step(self, timed_events=None):
+        fs, fm = self.build()
+        return self.lookups(fs, fm, self.d["coords0"], self.d["delta"], timed_events)
+
+
+def run_gpu(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    import stereoanywhere_b200 as sa
+
+    sa.CorrBlockB200.precision = args.precision
+    b, c, h, w = WORKLOADS[args.workload]
+    host, d = make_inputs(b, c, h, w, dev, seed=rank, pinned=True)
+    torch.cuda.synchronize()
+    path = GpuPath(sa, d, args.variant)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        path.step()
+    graph = None
+    if args.graph:
+        # capture the launch-bound step (36 launches of ~10-100 us) once; replay per step
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g_out = path.step()
+        for _ in range(2):
+            graph.replay()
+    barrier()
+    path.launches = 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lk_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gathered = None
+    e0.record()
+    for k in range(args.steps):
+        if graph is not None:
+            graph.replay()
+            out = g_out
+        else:
+            out = path.step(lk_events[k])
+        if dist is not None:  # the path's only collective: gather the quarter-res disparity
+            disp = out[2][:, :1].contiguous()
+            gathered = [torch.empty_like(disp) for _ in range(world)]
+            dist.all_gather(gathered, disp)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = path.launches if graph is None else args.steps * (36 if args.variant == "fused" else 69)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # dominant kernel (lookup) timed live: inside the timed region when eager; for the graph run a
+    # separate event-bracketed eager pass of the same launches follows (events cannot sit in a replay)
+    if graph is not None:
+        fs, fm = path.build()
+        torch.cuda.synchronize()
+        lk_events = []
+        for _ in range(args.steps):
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            path.lookups(fs, fm, d["coords0"], d["delta"], ev)
+            lk_events.append(ev)
+        torch.cuda.synchronize()
+    lk_ms = sum(a.elapsed_time(bb) for a, bb in lk_events) / args.steps
+    n_lk_launch = ITERS if args.variant == "fused" else 2 * ITERS
+    lk_launch_ms = lk_ms / n_lk_launch
+
+    # ---- end to end through the public API from pinned host buffers ---------------------------
+    keys = ["fl", "fr", "nl", "nr", "coords0", "delta", "tdisp", "tconf"]
+    dd = {k: torch.empty_like(d[k]) for k in keys}
+    res_s = torch.empty((b, LEVELS * (2 * RADIUS + 1), h, w), dtype=torch.float32).pin_memory()
+    res_m = torch.empty_like(res_s).pin_memory()
+    h2d = sum(host[k].numel() * 4 for k in keys)
+    d2h = res_s.numel() * 4 * 2
+    e2e_path = GpuPath(sa, dd, args.variant)
+
+    def e2e_step():
+        for k in keys:
+            dd[k].copy_(host[k], non_blocking=True)
+        s, m, _ = e2e_path.step()
+        res_s.copy_(s, non_blocking=True)
+        res_m.copy_(m, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+
+    def maxr(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_total, e2e_ms, lk_launch_ms = maxr(ms_total), maxr(max(e2e_ms, 0.0)), maxr(lk_launch_ms)
+    ms_step = ms_total / args.steps
+    value = world * b / (ms_step / 1e3)
+    e2e_value = world * b / (e2e_ms / args.steps / 1e3)
+
+    result = None
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        p = b * h * w
+        alg = (612 if args.variant == "fused" else 308) * p
+        achieved = alg / (lk_launch_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "lookup_vec_kernel" + ("<NV=2>" if args.variant == "fused" else "<NV=1>"),
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": TRAFFIC_BYTES.get((args.workload, args.variant)), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "launch_us": round(lk_launch_ms * 1e3, 2),
+                "path_algorithmic_gbs": round(path_bytes(b, c, h, w) / (ms_step * 1e-3) / 1e9, 1)}
+        cpu = None if args.no_cpu_baseline else cpu_baseline(args.workload, sample_pairs=args.cpu_pairs, reps=1)
+        result = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": f"{args.precision} corr (fp32 accumulate), f32 pyramid/lookup",
+            "data": "synthetic (seeded N(0,1) features, unit normals, U(0,W/4) disparities)",
+            "config": {"workload": args.workload, "pairs_per_gpu": b, "C": c, "H4": h, "W4": w, "iters": ITERS,
+                       "levels": LEVELS, "radius": RADIUS, "variant": args.variant, "cuda_graph": bool(args.graph),
+                       "l2": "inputs+volumes (>1 GB/step) exceed the 126 MB L2; no explicit flush",
+                       "parallelism": f"batch-sharded x{world}, all_gather of quarter-res disparity"},
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(e2e_ms / args.steps, 4), "wall_ms_per_step": round(e2e_wall / args.steps, 4)},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(result), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+# ncu --set full capture (profiles/); None until a capture for that workload exists.
+TRAFFIC_BYTES = {}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU: the reference's op sequence (oracle port)
+# ------------------------------------------------------------------------------------------
+
+def cpu_once(workload, pairs):
+    from oracle import corr_oracle as O
+
+    b, c, h, w = WORKLOADS[workload]
+    pairs = min(pairs, b)
+    host, _ = make_inputs(pairs, c, h, w, None, seed=0)
+    coords = [host["coords0"] + k * host["delta"] for k in range(ITERS)]
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.run_path_cpu(host["fl"], host["fr"], host["nl"], host["nr"], coords,
+                       trunc=(host["tdisp"], host["tconf"], 0.9), radius=RADIUS, num_levels=LEVELS)
+    return time.perf_counter() - t0, pairs
+
+
+def cpu_baseline(workload, sample_pairs=2, reps=1):
+    torch.set_num_threads(os.cpu_count() or 1)
+    cpu_once(workload, 1)  # warm-up (thread pool, allocator)
+    best = None
+    for _ in range(reps):
+        dt, pairs = cpu_once(workload, sample_pairs)
+        best = dt if best is None else min(best, dt)
+    return {"value": round(pairs / best, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{pairs} of {WORKLOADS[workload][0]} pairs of {workload}, all {ITERS} iterations, "
+                      f"oracle/corr_oracle.run_path_cpu (reference ATen op sequence), {best:.2f} s",
+            "host_cpus": os.cpu_count()}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    b = WORKLOADS[args.workload][0]
+    pairs = min(args.cpu_pairs, b)
+    for _ in range(min(args.warmup, 1)):
+        cpu_once(args.workload, pairs)
+    t = 0.0
+    for _ in range(args.steps):
+        dt, _ = cpu_once(args.workload, pairs)
+        t += dt
+    value = pairs * args.steps / t
+    sample = (f"each step = {pairs} of {b} pairs of {args.workload}, all {ITERS} iterations, oracle port of the "
+              f"reference op sequence (einsum, avg_pool2d, grid_sample) on CPU")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(t / args.steps * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "pairs_per_step": pairs, "iters": ITERS, "levels": LEVELS, "radius": RADIUS},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--variant", default="fused", choices=["fused", "protocol"],
+                    help="fused: truncate= / mono_corr / lookup_pair entry points; protocol: the reference's exact call sequence")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"], help="stereo correlation kernel")
+    ap.add_argument("--graph", type=int, default=0, help="replay the step from a CUDA graph in the device-resident run")
+    ap.add_argument("--cpu-pairs", type=int, default=2, help="pairs in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,135 @@
+/*
+ * sa_b200.h - C ABI of the B200-native Stereo Anywhere cost-volume path.
+ *
+ * One shared library (stereoanywhere_b200/lib/libsa_b200.so), plain pointers and sizes, no
+ * torch / C++ types.  Every pointer is a DEVICE pointer unless the parameter name starts with
+ * `h_` (host array, read synchronously before the call returns).  `stream` is a
+ * `cudaStream_t` passed as `void*` (NULL = legacy default stream).  Launches are asynchronous;
+ * nothing here synchronises the device or the host.
+ *
+ * Return value: 0 on success; > 0 is a `cudaError_t` from the launch; < 0 is one of the
+ * SA_E_* argument errors below.  `sa_last_error()` returns a thread-local description.
+ * The functions never throw and never fall back to a CPU path.
+ *
+ * The reference (kei312/stereoanywhere) has no FFI of its own - its "operator API" for this
+ * path is a Python class protocol (`models/stereoanywhere/corr.py:75-132`).  Each entry point
+ * cites the reference lines it replaces; `INTEGRATION.md` shows the ctypes binding and the
+ * three-line patch that selects this block inside `StereoAnywhere.forward`
+ * (`models/stereoanywhere/stereoanywhere.py:128-133`).
+ *
+ * Tensor layouts are the reference's: feature maps NCHW fp32, volumes [B,H,W2,1,W3] fp32
+ * (flattened here to rows = B*H*W2 of W3 floats), lookup output [B, L*(2r+1), H, W] fp32.
+ */
+#ifndef SA_B200_H
+#define SA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SA_ABI_VERSION 1
+#define SA_MAX_LEVELS 8   /* pyramid levels a lookup can address */
+#define SA_MAX_BINS 32    /* depth bins of sa_masked_volume */
+
+#define SA_E_INVALID (-1)     /* bad size / null pointer */
+#define SA_E_ALIGN (-2)       /* pointer or pitch not aligned as documented */
+#define SA_E_UNSUPPORTED (-3) /* shape outside what the kernel family covers */
+
+int sa_abi_version(void);
+const char* sa_last_error(void);
+
+/* ---------------------------------------------------------------- A1 / A2: correlation volume
+ * vol[b,h,w2,w3] = (sum_c L[b,c,h,w2] * R[b,c,h,w3]) / divisor * post_scale
+ * Replaces `CorrBlock1D.corr` (corr.py:117-132: einsum, / sqrt(C)) and the `1.73 *` of
+ * stereoanywhere.py:136 (post_scale).  fmap_l is [B,C,H,W2], fmap_r is [B,C,H,W3], both
+ * contiguous fp32; vol is rows = B*H*W2 by W3 floats, contiguous.
+ *
+ * sa_corr_fp32  : SIMT fp32 FMA, any C >= 1 (the mono C=3 volume is a pure streaming write).
+ * sa_corr_tf32  : tcgen05 kind::tf32, operands TMA-staged straight from NCHW (MN-major), fp32
+ *                 accumulate in TMEM.  Needs C % 8 == 0, W2 % 4 == 0, W3 % 4 == 0, W3 <= 1024,
+ *                 16-byte aligned pointers.  Normwise error <= 1e-3 of max|vol|.
+ * If pyr1..pyr3 are non-NULL (all three or none) the avg-pooled levels 1..3 of
+ * `CorrBlock1D.__init__` (corr.py:88-91) are written by the same kernel (row pitches pitchN in
+ * floats, multiples of 4; requires W3 % 8 == 0).
+ * If trunc_disp/trunc_conf are non-NULL ([B,1,H,W2] each) the stored volume (and its pyramid)
+ * is T * vol with T of `truncate_corr_volume_v2` (utils/utils.py:231-236, stereoanywhere.py:
+ * 253-255), trunc_gain = attenuation gain.
+ */
+int sa_corr_fp32(const float* fmap_l, const float* fmap_r, float* vol, int B, int C, int H, int W2, int W3,
+                 float divisor, float post_scale, void* stream);
+
+int sa_corr_tf32(const float* fmap_l, const float* fmap_r, float* vol, int B, int C, int H, int W2, int W3,
+                 float divisor, float post_scale, const float* trunc_disp, const float* trunc_conf,
+                 double trunc_gain, float* pyr1, float* pyr2, float* pyr3, int64_t pitch1, int64_t pitch2,
+                 int64_t pitch3, void* stream);
+
+/* ---------------------------------------------------------------- A3: avg-pooled pyramid
+ * dst_k[row, j] = 0.5 * (prev[row, 2j] + prev[row, 2j+1]),  j < floor(W_prev / 2)
+ * Replaces the avg_pool2d chain of `CorrBlock1D.__init__` (corr.py:76-91).  Builds n_out (1..3)
+ * further levels from `src` (rows x W floats, row pitch src_pitch floats) in ONE pass over
+ * `src`.  dst pitches are in floats.  The reference's dead (L+1)-th level is not built.
+ * Optional truncation (A5): if trunc_disp != NULL, `masked0` (rows x W, pitch = W) receives
+ * T * src and the levels are pooled from the masked values; trunc_disp / trunc_conf hold one
+ * float per row (the [B,1,H,W2] maps flattened), `w2_size` = W2 (left-image width).
+ * Fast path: W % 8 == 0, pitches % 4 == 0, 16-byte aligned pointers; anything else takes the
+ * generic (scalar) kernel - still on the GPU.
+ */
+int sa_pyramid(const float* src, int64_t rows, int W, int64_t src_pitch, int n_out, float* dst1, float* dst2,
+               float* dst3, int64_t pitch1, int64_t pitch2, int64_t pitch3, const float* trunc_disp,
+               const float* trunc_conf, double trunc_gain, int w2_size, float* masked0, void* stream);
+
+/* ---------------------------------------------------------------- A4: multi-level lookup
+ * For level i < L, tap k in [-r, r]:  xs = (coords[b,0,h,w] + pad0) / 2^i + k,
+ *   out[b, i*(2r+1) + k + r, h, w - pad0] = (1-f) * tap(P_i[b,h,w,:], x0) + f * tap(.., x0+1),
+ *   x0 = floor(xs), f = xs - x0, tap = 0 outside [0, W_i).
+ * Replaces `CorrBlock1D.__call__` + `bilinear_sampler` (corr.py:93-115, utils/utils.py:19-35).
+ * h_levels / h_widths / h_pitches are HOST arrays of length num_levels (device pointers,
+ * valid widths W_i, row pitches in floats).  coords is [B,2,H,W] (only channel 0 is read;
+ * coords_bstride = floats between batches, 2*H*W for a contiguous tensor).  out is
+ * [B, L*(2r+1), H, W - pad0 - pad1] contiguous.
+ * Fast path (warp-cooperative 128-bit loads): radius <= 5, L <= 4, pad = 0, all pitches % 4 == 0,
+ * 16-byte aligned level pointers.  Otherwise a generic kernel runs.
+ */
+int sa_lookup(const float* const* h_levels, const int* h_widths, const int64_t* h_pitches, int num_levels,
+              int radius, const float* coords, int64_t coords_bstride, float* out, int B, int H, int W,
+              int pad0, int pad1, void* stream);
+
+/* Same, two volumes (stereo + mono) with one read of coords and one launch
+ * (the two calls of stereoanywhere.py:270-271).  Both volumes share L, r and geometry. */
+int sa_lookup2(const float* const* h_levels_a, const float* const* h_levels_b, const int* h_widths,
+               const int64_t* h_pitches_a, const int64_t* h_pitches_b, int num_levels, int radius,
+               const float* coords, int64_t coords_bstride, float* out_a, float* out_b, int B, int H, int W,
+               void* stream);
+
+/* ---------------------------------------------------------------- A5: truncation mask (standalone)
+ * mask[b,h,w2,w3] = (1-c) + c * (sigmoid((w2 - d) - w3) * (1-g) + g); writes `out` = mask * vol
+ * when vol != NULL, else the mask itself.  Replaces `truncate_corr_volume_v2`
+ * (utils/utils.py:216-238) and the product of stereoanywhere.py:253-255. */
+int sa_truncate(const float* vol, const float* disp, const float* conf, double gain, float* out, int64_t rows,
+                int W2, int W3, void* stream);
+
+/* ---------------------------------------------------------------- A6: depth-bin masked volume
+ * out[b,n,h,w2,w3] = vol[b,h,w2,w3] if bin(mde_l[b,h,w2]) == bin(mde_r[b,h,w3]) == n else 0,
+ * bin(x) = n iff h_edges[n] <= x < h_edges[n+1]  (h_edges: HOST array of n_bins+1 floats;
+ * the reference's edges are float32(i / N)).  Replaces `generate_masks` + the two broadcast
+ * products (utils/utils.py:48-54, stereoanywhere.py:138-139,161).
+ * If vol == NULL the volume is computed on the fly from unit normals normals_l / normals_r
+ * ([B,3,H,W]) as in A2 (divisor, post_scale). */
+int sa_masked_volume(const float* vol, const float* normals_l, const float* normals_r, float divisor,
+                     float post_scale, const float* mde_l, const float* mde_r, const float* h_edges, int n_bins,
+                     float* out, int B, int H, int W2, int W3, void* stream);
+
+/* ---------------------------------------------------------------- A7: training-only corruption
+ * mode 0 (roll):  out = vol*(1-m) + roll(vol, shift, dim=W2)*m
+ * mode 1 (noise): out = vol*(1-m) + vol*noise[b,h,w2]*m
+ * mode 2 (gauss): out = vol*(1-m) + vol*(k*exp(-(w2-w3)^2/2))*m
+ * m = bin_mask[b,h,w2] in {0,1}.  Replaces stereoanywhere.py:214-251 (+ utils/utils.py:200-214). */
+int sa_corrupt(const float* vol, const float* bin_mask, int mode, int shift, const float* noise, float gauss_k,
+               float* out, int B, int H, int W2, int W3, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SA_B200_H */

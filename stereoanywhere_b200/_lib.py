@@ -1,0 +1,81 @@
+"""ctypes binding of the C-ABI library (include/sa_b200.h).
+
+There is no CPU fallback: if `lib/libsa_b200.so` is missing and cannot be built, importing the
+ops raises.  Signatures below mirror include/sa_b200.h one to one.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libsa_b200.so")
+
+_lib = None
+
+c_fp = C.c_void_p  # device pointers travel as integers (tensor.data_ptr())
+
+
+class SaError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    i, i64, f, d, vp = C.c_int, C.c_int64, C.c_float, C.c_double, C.c_void_p
+    lib.sa_abi_version.restype = i
+    lib.sa_abi_version.argtypes = []
+    lib.sa_last_error.restype = C.c_char_p
+    lib.sa_last_error.argtypes = []
+    lib.sa_corr_fp32.restype = i
+    lib.sa_corr_fp32.argtypes = [vp, vp, vp, i, i, i, i, i, f, f, vp]
+    lib.sa_corr_tf32.restype = i
+    lib.sa_corr_tf32.argtypes = [vp, vp, vp, i, i, i, i, i, f, f, vp, vp, d, vp, vp, vp, i64, i64, i64, vp]
+    lib.sa_pyramid.restype = i
+    lib.sa_pyramid.argtypes = [vp, i64, i, i64, i, vp, vp, vp, i64, i64, i64, vp, vp, d, i, vp, vp]
+    lib.sa_lookup.restype = i
+    lib.sa_lookup.argtypes = [C.POINTER(vp), C.POINTER(i), C.POINTER(i64), i, i, vp, i64, vp, i, i, i, i, i, vp]
+    lib.sa_lookup2.restype = i
+    lib.sa_lookup2.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(i), C.POINTER(i64), C.POINTER(i64), i, i,
+                               vp, i64, vp, vp, i, i, i, vp]
+    lib.sa_truncate.restype = i
+    lib.sa_truncate.argtypes = [vp, vp, vp, d, vp, i64, i, i, vp]
+    lib.sa_masked_volume.restype = i
+    lib.sa_masked_volume.argtypes = [vp, vp, vp, f, f, vp, vp, C.POINTER(f), i, vp, i, i, i, i, vp]
+    lib.sa_corrupt.restype = i
+    lib.sa_corrupt.argtypes = [vp, vp, i, i, vp, f, vp, i, i, i, i, vp]
+
+
+EXPORTS = [
+    "sa_abi_version", "sa_last_error", "sa_corr_fp32", "sa_corr_tf32", "sa_pyramid", "sa_lookup", "sa_lookup2",
+    "sa_truncate", "sa_masked_volume", "sa_corrupt",
+]
+
+
+def load():
+    """Load (building first if the .so is absent and nvcc is present). Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc, compile error ...
+            raise SaError(
+                f"stereoanywhere_b200: CUDA library {LIB_PATH} is missing and could not be built ({e}). "
+                "There is no CPU fallback; run `python -m stereoanywhere_b200.build`."
+            ) from e
+    lib = C.CDLL(LIB_PATH)
+    _declare(lib)
+    if lib.sa_abi_version() != 1:
+        raise SaError("stereoanywhere_b200: ABI version mismatch between _lib.py and libsa_b200.so")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().sa_last_error().decode(errors="replace")
+        kind = "CUDA error" if rc > 0 else "argument error"
+        raise SaError(f"{what}: {kind} {rc}: {msg}")

@@ -1,0 +1,151 @@
+"""`CorrBlockB200` - drop-in for the reference's correlation block.
+
+Same protocol as `CorrBlock1D` (reference models/stereoanywhere/corr.py:75-132): a static
+`corr(fmapL, fmapR)`, a constructor taking the `[B,H,W2,1,W3]` volume with `num_levels`, `radius`,
+`pad`, and `__call__(coords)` returning `[B, num_levels*(2*radius+1), H, W]`.  Selected inside the
+reference model by adding one branch at stereoanywhere.py:128-133, e.g.
+
+    elif self.args.corr_implementation == "b200":
+        corr_block = CorrBlockB200
+
+All arithmetic runs in the sm_100a kernels behind `torch.ops.sa_b200.*`; there is no CPU path
+and no autograd (the block raises under `requires_grad`).
+
+Beyond the strict protocol (used when the caller's wiring allows, reference call sites in
+brackets):
+  * `CorrBlockB200(vol, truncate=(disp, conf, gain))`  - builds the pyramid of T*vol in the same
+    pass that forms the product  [stereoanywhere.py:203, 253-255];
+  * `CorrBlockB200.mono_corr(nL, nR)`                  - A2 with the `1.73 *` folded in  [:136];
+  * `CorrBlockB200.lookup_pair(stereo_fn, mono_fn, coords)` - both per-iteration lookups in one
+    launch  [:270-271];
+  * `masked_volume(...)`, `truncation_mask(...)`, `corrupt_volume(...)` - A6 / A5 / A7.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+_OPS = torch.ops.sa_b200
+
+
+def _no_grad_check(*tensors):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            "CorrBlockB200 is forward-only: inputs must not require grad (wrap the call in torch.no_grad()); "
+            "the reference path's backward is not part of this build")
+
+
+class CorrBlockB200:
+    """B200-native correlation block; see module docstring."""
+
+    #: precision of `corr()` for the stereo volume: "tf32" (tcgen05) or "fp32" (SIMT FMA);
+    #: SA_B200_PRECISION overrides the default at import time.
+    precision = os.environ.get("SA_B200_PRECISION", "tf32")
+
+    def __init__(self, fullcorr: torch.Tensor, num_levels: int = 4, radius: int = 4, pad: Sequence[int] = (0, 0), *,
+                 truncate: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None):
+        _no_grad_check(fullcorr)
+        if fullcorr.dim() != 5 or fullcorr.shape[3] != 1:
+            raise ValueError("fullcorr must be [B, H, W2, 1, W3] (reference corr.py:86)")
+        self.num_levels = num_levels
+        self.radius = radius
+        self.pad = list(pad)
+        b, h, w2, _, w3 = fullcorr.shape
+        if not fullcorr.is_contiguous():
+            fullcorr = fullcorr.contiguous()
+        rows = fullcorr.view(b * h * w2, w3)
+        if truncate is not None:
+            disp, conf, gain = truncate
+            levels = _OPS.pyramid(rows, num_levels, disp, conf, float(gain))
+            self.fullcorr = levels[0].view(b, h, w2, 1, w3)
+        else:
+            levels = _OPS.pyramid(rows, num_levels, None, None, 0.0)
+            self.fullcorr = fullcorr
+        self._levels: List[torch.Tensor] = list(levels)
+        self._widths: List[int] = ops.level_widths(w3, num_levels)
+        self._shape = (b, h, w2)
+
+    @property
+    def corr_pyramid(self) -> List[torch.Tensor]:
+        """Levels as `[B*H*W2, 1, 1, W3_i]` views like the reference attribute (corr.py:87-91).
+        (Levels >= 1 are views into 16-byte-pitched rows; the reference's dead extra level is absent.)"""
+        return [lv[:, :w].unsqueeze(1).unsqueeze(1) for lv, w in zip(self._levels, self._widths)]
+
+    def __call__(self, coords: torch.Tensor) -> torch.Tensor:
+        _no_grad_check(coords)
+        dt = coords.dtype
+        if dt != torch.float32:
+            coords = coords.float()
+        out = _OPS.lookup(self._levels, self._widths, coords, self.radius, self.pad[0], self.pad[1])
+        return out if dt == torch.float32 else out.to(dt)
+
+    # ---- protocol: static corr --------------------------------------------------------------
+    @staticmethod
+    def corr(fmap2: torch.Tensor, fmap3: torch.Tensor) -> torch.Tensor:
+        """[B,C,H,W2] x [B,C,H,W3] -> [B,H,W2,1,W3], divided by sqrt(C) (reference corr.py:117-132).
+
+        C % 8 == 0 and 4-aligned widths take the tensor-core kernel in `CorrBlockB200.precision`;
+        anything else (the C=3 normals volume in particular) takes the fp32 SIMT kernel."""
+        _no_grad_check(fmap2, fmap3)
+        dt = fmap2.dtype
+        f2, f3 = fmap2.float(), fmap3.float()
+        prec = CorrBlockB200.precision
+        c, w2, w3 = f2.shape[1], f2.shape[3], f3.shape[3]
+        if prec != "fp32" and not (c % 8 == 0 and c >= 32 and w2 % 4 == 0 and w3 % 4 == 0 and w3 <= 1024):
+            prec = "fp32"
+        vol = _OPS.corr_volume(f2, f3, prec, 1.0)
+        return vol if dt == torch.float32 else vol.to(dt)
+
+    # ---- beyond the protocol ------------------------------------------------------------------
+    @staticmethod
+    def mono_corr(normals2: torch.Tensor, normals3: torch.Tensor, gain: float = 1.73) -> torch.Tensor:
+        """`1.73 * corr(nL, nR)` in one pass (stereoanywhere.py:136)."""
+        _no_grad_check(normals2, normals3)
+        return _OPS.corr_volume(normals2.float(), normals3.float(), "fp32", float(gain))
+
+    @staticmethod
+    def lookup_pair(block_a: "CorrBlockB200", block_b: "CorrBlockB200", coords: torch.Tensor):
+        """`(block_a(coords), block_b(coords))` with one launch (stereoanywhere.py:270-271)."""
+        _no_grad_check(coords)
+        if (block_a.radius != block_b.radius or block_a._widths != block_b._widths
+                or block_a.pad != [0, 0] or block_b.pad != [0, 0]):
+            return block_a(coords), block_b(coords)
+        dt = coords.dtype
+        if dt != torch.float32:
+            coords = coords.float()
+        oa, ob = _OPS.lookup2(block_a._levels, block_b._levels, block_a._widths, coords, block_a.radius)
+        return (oa, ob) if dt == torch.float32 else (oa.to(dt), ob.to(dt))
+
+
+def truncation_mask(disp: torch.Tensor, conf: torch.Tensor, attenuation_gain: float,
+                    vol: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`truncate_corr_volume_v2(disp, conf, conf_th=None, attenuation_gain)` (utils/utils.py:216-238);
+    with `vol` ([B,1,H,W2,W3]) returns the product `mask * vol` of stereoanywhere.py:253-255."""
+    _no_grad_check(disp, conf, vol)
+    return _OPS.truncate(vol, disp, conf, float(attenuation_gain))
+
+
+def masked_volume(vol: torch.Tensor, mde_l: torch.Tensor, mde_r: torch.Tensor, n_bins: int = 8) -> torch.Tensor:
+    """`vol * generate_masks(mdeL,N).unsqueeze(4) * generate_masks(mdeR,N).unsqueeze(3)`:
+    [B,1,H,W2,W3] -> [B,N,H,W2,W3] (utils/utils.py:48-54, stereoanywhere.py:138-139,161)."""
+    _no_grad_check(vol)
+    return _OPS.masked_volume(vol, None, None, 1.0, mde_l, mde_r, n_bins)
+
+
+def masked_mono_volume(normals_l: torch.Tensor, normals_r: torch.Tensor, mde_l: torch.Tensor, mde_r: torch.Tensor,
+                       n_bins: int = 8, gain: float = 1.73) -> torch.Tensor:
+    """A2 + A6 fused: the hourglass input straight from the normal maps (the mono volume is never
+    materialised on its own)."""
+    _no_grad_check(normals_l, normals_r)
+    return _OPS.masked_volume(None, normals_l, normals_r, float(gain), mde_l, mde_r, n_bins)
+
+
+def corrupt_volume(vol: torch.Tensor, bin_mask: torch.Tensor, mode: str, *, shift: int = 0,
+                   noise: Optional[torch.Tensor] = None, gauss_k: float = 0.0) -> torch.Tensor:
+    """Training-only corruption blends of stereoanywhere.py:214-251 (`mode` = roll | noise | gauss)."""
+    code = {"roll": 0, "noise": 1, "gauss": 2}[mode]
+    return _OPS.corrupt(vol, bin_mask, code, int(shift), noise, float(gauss_k))

@@ -1,0 +1,32 @@
+// Library-level pieces of the C ABI: version, thread-local error text, device properties.
+#include <stdarg.h>
+
+#include "sa_common.cuh"
+
+namespace sa {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static thread_local int cached_dev = -1, cached = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+}  // namespace sa
+
+extern "C" int sa_abi_version(void) { return SA_ABI_VERSION; }
+extern "C" const char* sa_last_error(void) { return sa::g_err; }

@@ -1,0 +1,286 @@
+"""torch custom ops (`torch.ops.sa_b200.*`) over the C-ABI library.
+
+Host code is plumbing only: argument checks, output allocation from torch's caching allocator,
+the current CUDA stream, one ctypes call.  No CPU implementation is registered - calling an op
+with CPU tensors raises (the dispatcher has no CPU kernel), and a missing `libsa_b200.so` raises
+at first use.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+MAX_LEVELS = 8
+_PYR_ALIGN = 4  # floats: level pitches are multiples of 16 bytes so the lookup can use 128-bit loads
+
+
+def _stream_ptr(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _req(cond: bool, msg: str):
+    if not cond:
+        raise ValueError(msg)
+
+
+def _cuda_f32(t: torch.Tensor, name: str):
+    _req(t.is_cuda, f"{name} must be a CUDA tensor (stereoanywhere_b200 has no CPU path)")
+    _req(t.dtype == torch.float32, f"{name} must be float32, got {t.dtype}")
+
+
+def level_widths(w: int, num_levels: int) -> List[int]:
+    """Valid widths of the pyramid levels (floor halving, reference corr.py:88-91)."""
+    out = [w]
+    for _ in range(num_levels - 1):
+        out.append(out[-1] // 2)
+    return out
+
+
+def level_pitch(w: int) -> int:
+    return (w + _PYR_ALIGN - 1) // _PYR_ALIGN * _PYR_ALIGN
+
+
+# ------------------------------------------------------------------------------------------
+# implementations (CUDA only)
+# ------------------------------------------------------------------------------------------
+
+
+def _corr_volume(fmap_l: torch.Tensor, fmap_r: torch.Tensor, precision: str, post_scale: float) -> torch.Tensor:
+    _cuda_f32(fmap_l, "fmap_l")
+    _cuda_f32(fmap_r, "fmap_r")
+    _req(fmap_l.dim() == 4 and fmap_r.dim() == 4, "feature maps must be [B,C,H,W]")
+    b, c, h, w2 = fmap_l.shape
+    _req(fmap_r.shape[:3] == (b, c, h), "left/right feature maps must share B, C, H")
+    w3 = fmap_r.shape[3]
+    fmap_l = fmap_l.contiguous()
+    fmap_r = fmap_r.contiguous()
+    vol = torch.empty((b, h, w2, 1, w3), dtype=torch.float32, device=fmap_l.device)
+    # the reference divides by torch.sqrt(torch.tensor(C)): a float32 scalar (corr.py:132)
+    divisor = float(torch.sqrt(torch.tensor(c)))
+    lib = _lib.load()
+    with torch.cuda.device(fmap_l.device):
+        if precision == "fp32":
+            rc = lib.sa_corr_fp32(fmap_l.data_ptr(), fmap_r.data_ptr(), vol.data_ptr(), b, c, h, w2, w3, divisor,
+                                  post_scale, _stream_ptr(vol))
+        elif precision == "tf32":
+            rc = lib.sa_corr_tf32(fmap_l.data_ptr(), fmap_r.data_ptr(), vol.data_ptr(), b, c, h, w2, w3, divisor,
+                                  post_scale, None, None, 0.0, None, None, None, 0, 0, 0, _stream_ptr(vol))
+        else:
+            raise ValueError(f"unknown precision {precision!r} (use 'tf32' or 'fp32')")
+    _lib.check(rc, f"sa_corr_{precision}")
+    return vol
+
+
+def _pyramid(vol: torch.Tensor, num_levels: int, trunc_disp: Optional[torch.Tensor],
+             trunc_conf: Optional[torch.Tensor], trunc_gain: float) -> List[torch.Tensor]:
+    """vol: [rows, W] (contiguous view of the block's volume). Returns levels [rows, pitch_i];
+    level 0 is `vol` itself, or the truncated product when trunc_* are given."""
+    _cuda_f32(vol, "fullcorr")
+    _req(vol.dim() == 2 and vol.is_contiguous(), "pyramid expects a contiguous [rows, W] view")
+    _req(1 <= num_levels <= MAX_LEVELS, f"num_levels must be in 1..{MAX_LEVELS}")
+    rows, w = vol.shape
+    widths = level_widths(w, num_levels)
+    _req(widths[-1] >= 1, f"volume width {w} is too small for {num_levels} levels")
+    lib = _lib.load()
+    dev = vol.device
+    trunc = trunc_disp is not None
+    levels = [vol]
+    if trunc:
+        _cuda_f32(trunc_disp, "trunc_disp")
+        _cuda_f32(trunc_conf, "trunc_conf")
+        trunc_disp = trunc_disp.contiguous()
+        trunc_conf = trunc_conf.contiguous()
+        _req(trunc_disp.numel() == rows and trunc_conf.numel() == rows,
+             "truncation maps must be [B,1,H,W2] matching the volume")
+        w2_size = trunc_disp.shape[-1]
+        levels = [torch.empty_like(vol)]
+    with torch.cuda.device(dev):
+        st = _stream_ptr(vol)
+        if num_levels == 1:
+            if trunc:
+                rc = lib.sa_truncate(vol.data_ptr(), trunc_disp.data_ptr(), trunc_conf.data_ptr(), trunc_gain,
+                                     levels[0].data_ptr(), rows, w2_size, w, st)
+                _lib.check(rc, "sa_truncate")
+            return levels
+        src, src_w, src_pitch = vol, w, w
+        nxt = 1
+        first = True
+        while nxt < num_levels:
+            n_out = min(3, num_levels - nxt)
+            outs = [torch.empty((rows, level_pitch(widths[nxt + k])), dtype=torch.float32, device=dev)
+                    for k in range(n_out)]
+            ptr = [o.data_ptr() for o in outs] + [None] * (3 - n_out)
+            pit = [o.shape[1] for o in outs] + [0] * (3 - n_out)
+            if first and trunc:
+                rc = lib.sa_pyramid(src.data_ptr(), rows, src_w, src_pitch, n_out, ptr[0], ptr[1], ptr[2], pit[0],
+                                    pit[1], pit[2], trunc_disp.data_ptr(), trunc_conf.data_ptr(), trunc_gain,
+                                    w2_size, levels[0].data_ptr(), st)
+            else:
+                rc = lib.sa_pyramid(src.data_ptr(), rows, src_w, src_pitch, n_out, ptr[0], ptr[1], ptr[2], pit[0],
+                                    pit[1], pit[2], None, None, 0.0, 0, None, st)
+            _lib.check(rc, "sa_pyramid")
+            levels.extend(outs)
+            nxt += n_out
+            src, src_w, src_pitch = outs[-1], widths[nxt - 1], outs[-1].shape[1]
+            first = False
+    return levels
+
+
+def _marshal(levels: Sequence[torch.Tensor], widths: Sequence[int]):
+    n = len(levels)
+    _req(1 <= n <= MAX_LEVELS and len(widths) == n, f"need 1..{MAX_LEVELS} levels with matching widths")
+    rows = levels[0].shape[0]
+    for t in levels:
+        _cuda_f32(t, "pyramid level")
+        _req(t.dim() == 2 and t.stride(1) == 1 and t.shape[0] == rows, "pyramid levels must be [rows, pitch] row-major")
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in levels])
+    wid = (C.c_int * n)(*widths)
+    pit = (C.c_int64 * n)(*[t.stride(0) for t in levels])
+    return n, ptrs, wid, pit
+
+
+def _coords_view(coords: torch.Tensor):
+    _cuda_f32(coords, "coords")
+    _req(coords.dim() == 4 and coords.shape[1] >= 1, "coords must be [B,2,H,W]")
+    b, _, h, w = coords.shape
+    if not (coords.stride(3) == 1 and coords.stride(2) == w):
+        coords = coords.contiguous()
+    return coords, b, h, w
+
+
+def _lookup(levels: Sequence[torch.Tensor], widths: Sequence[int], coords: torch.Tensor, radius: int, pad0: int,
+            pad1: int) -> torch.Tensor:
+    coords, b, h, w = _coords_view(coords)
+    n, ptrs, wid, pit = _marshal(levels, widths)
+    _req(levels[0].shape[0] == b * h * w, "coords do not match the volume this block was built from")
+    _req(0 <= pad0 and 0 <= pad1 and pad0 + pad1 < w, "bad pad")
+    out = torch.empty((b, n * (2 * radius + 1), h, w - pad0 - pad1), dtype=torch.float32, device=coords.device)
+    lib = _lib.load()
+    with torch.cuda.device(coords.device):
+        rc = lib.sa_lookup(ptrs, wid, pit, n, radius, coords.data_ptr(), coords.stride(0), out.data_ptr(), b, h, w,
+                           pad0, pad1, _stream_ptr(coords))
+    _lib.check(rc, "sa_lookup")
+    return out
+
+
+def _lookup2(levels_a: Sequence[torch.Tensor], levels_b: Sequence[torch.Tensor], widths: Sequence[int],
+             coords: torch.Tensor, radius: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    coords, b, h, w = _coords_view(coords)
+    n, ptrs_a, wid, pit_a = _marshal(levels_a, widths)
+    nb, ptrs_b, _, pit_b = _marshal(levels_b, widths)
+    _req(n == nb, "lookup2 needs two pyramids with the same number of levels")
+    _req(levels_a[0].shape[0] == b * h * w and levels_b[0].shape[0] == b * h * w, "coords do not match the volumes")
+    out_a = torch.empty((b, n * (2 * radius + 1), h, w), dtype=torch.float32, device=coords.device)
+    out_b = torch.empty_like(out_a)
+    lib = _lib.load()
+    with torch.cuda.device(coords.device):
+        rc = lib.sa_lookup2(ptrs_a, ptrs_b, wid, pit_a, pit_b, n, radius, coords.data_ptr(), coords.stride(0),
+                            out_a.data_ptr(), out_b.data_ptr(), b, h, w, _stream_ptr(coords))
+    _lib.check(rc, "sa_lookup2")
+    return out_a, out_b
+
+
+def _truncate(vol: Optional[torch.Tensor], disp: torch.Tensor, conf: torch.Tensor, gain: float) -> torch.Tensor:
+    _cuda_f32(disp, "disp")
+    _cuda_f32(conf, "conf")
+    b, _, h, w2 = disp.shape
+    disp, conf = disp.contiguous(), conf.contiguous()
+    if vol is not None:
+        _cuda_f32(vol, "vol")
+        vol = vol.contiguous()
+        w3 = vol.shape[-1]
+        _req(vol.numel() == b * h * w2 * w3, "vol does not match disp")
+        out = torch.empty_like(vol)
+    else:
+        w3 = w2
+        out = torch.empty((b, 1, h, w2, w3), dtype=torch.float32, device=disp.device)
+    lib = _lib.load()
+    with torch.cuda.device(disp.device):
+        rc = lib.sa_truncate(vol.data_ptr() if vol is not None else None, disp.data_ptr(), conf.data_ptr(), gain,
+                             out.data_ptr(), b * h * w2, w2, w3, _stream_ptr(disp))
+    _lib.check(rc, "sa_truncate")
+    return out
+
+
+def bin_edges(n_bins: int):
+    """float32(i / N) for i = 0..N, as the reference's comparisons see them (utils/utils.py:51-53)."""
+    return (C.c_float * (n_bins + 1))(*[i / n_bins for i in range(n_bins + 1)])
+
+
+def _masked_volume(vol: Optional[torch.Tensor], normals_l: Optional[torch.Tensor], normals_r: Optional[torch.Tensor],
+                   post_scale: float, mde_l: torch.Tensor, mde_r: torch.Tensor, n_bins: int) -> torch.Tensor:
+    _cuda_f32(mde_l, "mde_l")
+    _cuda_f32(mde_r, "mde_r")
+    b, _, h, w2 = mde_l.shape
+    w3 = mde_r.shape[-1]
+    mde_l, mde_r = mde_l.contiguous(), mde_r.contiguous()
+    out = torch.empty((b, n_bins, h, w2, w3), dtype=torch.float32, device=mde_l.device)
+    lib = _lib.load()
+    with torch.cuda.device(mde_l.device):
+        if vol is not None:
+            _cuda_f32(vol, "vol")
+            vol = vol.contiguous()
+            _req(vol.numel() == b * h * w2 * w3, "vol does not match the depth maps")
+            rc = lib.sa_masked_volume(vol.data_ptr(), None, None, 1.0, 1.0, mde_l.data_ptr(), mde_r.data_ptr(),
+                                      bin_edges(n_bins), n_bins, out.data_ptr(), b, h, w2, w3, _stream_ptr(out))
+        else:
+            _cuda_f32(normals_l, "normals_l")
+            _cuda_f32(normals_r, "normals_r")
+            _req(normals_l.shape == (b, 3, h, w2) and normals_r.shape == (b, 3, h, w3), "normals must be [B,3,H,W]")
+            normals_l, normals_r = normals_l.contiguous(), normals_r.contiguous()
+            divisor = float(torch.sqrt(torch.tensor(3)))
+            rc = lib.sa_masked_volume(None, normals_l.data_ptr(), normals_r.data_ptr(), divisor, post_scale,
+                                      mde_l.data_ptr(), mde_r.data_ptr(), bin_edges(n_bins), n_bins, out.data_ptr(),
+                                      b, h, w2, w3, _stream_ptr(out))
+    _lib.check(rc, "sa_masked_volume")
+    return out
+
+
+def _corrupt(vol: torch.Tensor, bin_mask: torch.Tensor, mode: int, shift: int, noise: Optional[torch.Tensor],
+             gauss_k: float) -> torch.Tensor:
+    _cuda_f32(vol, "vol")
+    _req(vol.dim() == 5 and vol.shape[1] == 1, "vol must be [B,1,H,W2,W3]")
+    b, _, h, w2, w3 = vol.shape
+    vol = vol.contiguous()
+    bin_mask = bin_mask.to(torch.float32).contiguous()
+    _req(bin_mask.numel() == b * h * w2, "bin_mask must be [B,1,H,W2]")
+    if noise is not None:
+        noise = noise.to(torch.float32).contiguous()
+        _req(noise.numel() == b * h * w2, "noise must be [B,1,H,W2,1]")
+    out = torch.empty_like(vol)
+    lib = _lib.load()
+    with torch.cuda.device(vol.device):
+        rc = lib.sa_corrupt(vol.data_ptr(), bin_mask.data_ptr(), mode, shift,
+                            noise.data_ptr() if noise is not None else None, gauss_k, out.data_ptr(), b, h, w2, w3,
+                            _stream_ptr(vol))
+    _lib.check(rc, "sa_corrupt")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# torch.library registration: functional ops, CUDA backend only
+# ------------------------------------------------------------------------------------------
+
+_LIBDEF = torch.library.Library("sa_b200", "DEF")
+_LIBDEF.define("corr_volume(Tensor fmap_l, Tensor fmap_r, str precision, float post_scale) -> Tensor")
+_LIBDEF.define("pyramid(Tensor vol_rows, int num_levels, Tensor? trunc_disp, Tensor? trunc_conf, float trunc_gain) -> Tensor[]")
+_LIBDEF.define("lookup(Tensor[] levels, int[] widths, Tensor coords, int radius, int pad0, int pad1) -> Tensor")
+_LIBDEF.define("lookup2(Tensor[] levels_a, Tensor[] levels_b, int[] widths, Tensor coords, int radius) -> (Tensor, Tensor)")
+_LIBDEF.define("truncate(Tensor? vol, Tensor disp, Tensor conf, float gain) -> Tensor")
+_LIBDEF.define("masked_volume(Tensor? vol, Tensor? normals_l, Tensor? normals_r, float post_scale, Tensor mde_l, Tensor mde_r, int n_bins) -> Tensor")
+_LIBDEF.define("corrupt(Tensor vol, Tensor bin_mask, int mode, int shift, Tensor? noise, float gauss_k) -> Tensor")
+
+_LIBDEF.impl("corr_volume", _corr_volume, "CUDA")
+_LIBDEF.impl("pyramid", _pyramid, "CUDA")
+_LIBDEF.impl("lookup", _lookup, "CUDA")
+_LIBDEF.impl("lookup2", _lookup2, "CUDA")
+_LIBDEF.impl("truncate", _truncate, "CUDA")
+_LIBDEF.impl("masked_volume", _masked_volume, "CUDA")
+_LIBDEF.impl("corrupt", _corrupt, "CUDA")
+
+OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "truncate", "masked_volume", "corrupt"]

@@ -1,0 +1,308 @@
+"""Parity of the CUDA path (through torch.ops.sa_b200 -> C ABI) against the oracle and the golden
+fixtures.  Everything here needs a B200; nothing reads /root/reference.
+
+Tolerances (north_star): correlation normwise max|d| / max|ref| <= 1e-3 for TF32 and <= 2e-6 for the
+fp32 SIMT kernel; lookup / pyramid / masks compare fp32 arithmetic and must agree to <= 2e-5
+absolute on O(1) data (grid_sample's normalise/un-normalise round trip alone is ~1e-5, SURVEY
+Appendix A); pyramid levels are bit-exact (halving is exact).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import corr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+WIDTH_TAGS = ["w24", "w39", "w40", "w50x34"]
+COORD_TAGS = ["left", "right", "far", "int"]
+
+
+def G(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.fixture(scope="module")
+def sa():
+    import stereoanywhere_b200 as sa_
+
+    return sa_
+
+
+def normwise(got, ref):
+    got = got.detach().double().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got, dtype=np.float64)
+    ref = ref.detach().double().cpu().numpy() if isinstance(ref, torch.Tensor) else np.asarray(ref, dtype=np.float64)
+    return np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30)
+
+
+def maxabs(got, ref):
+    got = got.detach().double().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got, dtype=np.float64)
+    ref = ref.detach().double().cpu().numpy() if isinstance(ref, torch.Tensor) else np.asarray(ref, dtype=np.float64)
+    return np.abs(got - ref).max()
+
+
+def make_coords(b, h, w, gen, kind="left"):
+    x = torch.arange(w, dtype=torch.float32).view(1, 1, 1, w).expand(b, 1, h, w)
+    y = torch.arange(h, dtype=torch.float32).view(1, 1, h, 1).expand(b, 1, h, w)
+    if kind == "left":
+        dx = -torch.rand(b, 1, h, w, generator=gen) * (w / 4)
+    else:
+        dx = torch.rand(b, 1, h, w, generator=gen) * 8
+    return torch.cat([x + dx, y], dim=1).contiguous()
+
+
+# ------------------------------------------------------------------------------------------ golden
+
+def test_golden_corr_fp32(sa, golden_path):
+    g = golden_path
+    sa.CorrBlockB200.precision = "fp32"
+    try:
+        v = sa.CorrBlockB200.corr(G(g["a1_fl"]), G(g["a1_fr"]))
+    finally:
+        sa.CorrBlockB200.precision = "tf32"
+    assert v.shape == g["a1_vol"].shape and v.dtype == torch.float32
+    assert normwise(v, g["a1_vol"]) < 2e-6
+    m = sa.CorrBlockB200.mono_corr(G(g["a2_nl"]), G(g["a2_nr"]))
+    assert normwise(m, g["a2_vol"]) < 2e-6
+    # protocol path for the mono volume: 1.73 * corr(normals) as the model writes it
+    m2 = 1.73 * sa.CorrBlockB200.corr(G(g["a2_nl"]), G(g["a2_nr"]))
+    assert normwise(m2, g["a2_vol"]) < 2e-6
+
+
+@pytest.mark.parametrize("tag", WIDTH_TAGS)
+def test_golden_pyramid_bit_exact(sa, golden_path, tag):
+    g = golden_path
+    blk = sa.CorrBlockB200(G(g[f"a3_{tag}_vol"]), num_levels=4, radius=4)
+    pyr = blk.corr_pyramid
+    assert len(pyr) == 4
+    for i, p in enumerate(pyr):
+        want = g[f"a3_{tag}_p{i}"]
+        assert tuple(p.shape) == want.shape
+        assert np.array_equal(p.cpu().numpy(), want), f"level {i}"
+
+
+@pytest.mark.parametrize("tag", WIDTH_TAGS)
+@pytest.mark.parametrize("ctag", COORD_TAGS)
+def test_golden_lookup(sa, golden_path, tag, ctag):
+    g = golden_path
+    blk = sa.CorrBlockB200(G(g[f"a3_{tag}_vol"]), num_levels=4, radius=4)
+    out = blk(G(g[f"a4_{tag}_{ctag}_coords"]))
+    want = g[f"a4_{tag}_{ctag}_out"]
+    assert tuple(out.shape) == want.shape and out.is_contiguous()
+    tol = 2e-4 if ctag == "far" else 3e-5  # 'far': |x| ~ 3W makes grid_sample's own coordinate noise larger
+    assert maxabs(out, want) < tol
+    # and against the float64 closed form, which has no grid_sample noise
+    levels = O.closed_pyramid(g[f"a3_{tag}_vol"][:, :, :, 0], 4)
+    closed = O.closed_lookup(levels, g[f"a4_{tag}_{ctag}_coords"][:, 0], radius=4)
+    assert maxabs(out, closed) < (2e-4 if ctag == "far" else 5e-6)
+
+
+def test_golden_lookup_radius_levels_pad(sa, golden_path):
+    g = golden_path
+    vol, coords = G(g["a4_alt_vol"]), G(g["a4_alt_coords"])
+    assert maxabs(sa.CorrBlockB200(vol, num_levels=2, radius=3)(coords), g["a4_alt_r3l2"]) < 3e-5
+    assert maxabs(sa.CorrBlockB200(vol, num_levels=3, radius=2)(coords), g["a4_alt_r2l3"]) < 3e-5
+    out = sa.CorrBlockB200(vol, num_levels=4, radius=4, pad=[2, 3])(coords)
+    assert tuple(out.shape) == (1, 36, 2, 27)
+    assert maxabs(out, g["a4_alt_pad23"]) < 3e-5
+
+
+def test_golden_truncation(sa, golden_path):
+    g = golden_path
+    d, c = G(g["a5_disp"]), G(g["a5_conf"])
+    assert maxabs(sa.truncation_mask(d, c, 0.9), g["a5_mask"]) < 1e-6
+    vol = G(g["a1_vol"])
+    prod = sa.truncation_mask(d, c, 0.9, vol=vol.squeeze(3).unsqueeze(1))
+    assert maxabs(prod.squeeze(1).unsqueeze(3), g["a5_product"]) < 2e-6
+    # fused: block built with truncate= has T*V as level 0 and pools it
+    blk = sa.CorrBlockB200(vol, num_levels=4, radius=4, truncate=(d, c, 0.9))
+    assert maxabs(blk.fullcorr, g["a5_product"]) < 2e-6
+    ref = O.closed_pyramid(g["a5_product"][:, :, :, 0], 4)
+    for lv, want in zip(blk.corr_pyramid, ref):
+        assert maxabs(lv.view(want.shape), want) < 2e-6
+
+
+def test_golden_masked_volume(sa, golden_path):
+    g = golden_path
+    mv = G(g["a2_vol"]).squeeze(3).unsqueeze(1)
+    out = sa.masked_volume(mv, G(g["a6_mde_l"]), G(g["a6_mde_r"]), 8)
+    assert tuple(out.shape) == g["a6_masked"].shape
+    assert np.array_equal(out.cpu().numpy(), g["a6_masked"])  # masks are 0/1: exact
+    fused = sa.masked_mono_volume(G(g["a2_nl"]), G(g["a2_nr"]), G(g["a6_mde_l"]), G(g["a6_mde_r"]), 8)
+    assert maxabs(fused, g["a6_masked"]) < 2e-6
+    assert np.array_equal((fused != 0).cpu().numpy(), g["a6_masked"] != 0)
+
+
+def test_golden_corruption(sa, golden_path):
+    g = golden_path
+    v5 = G(g["a1_vol"]).squeeze(3).unsqueeze(1)
+    m = G(g["a7_binmask"].astype(np.float32))
+    assert np.array_equal(sa.corrupt_volume(v5, m, "roll", shift=5).cpu().numpy(), g["a7_roll5"])
+    noise = G(g["a7_noise"].astype(np.float32))
+    assert maxabs(sa.corrupt_volume(v5, m, "noise", noise=noise), g["a7_noised"]) < 1e-6
+    k = float(v5.max())
+    assert maxabs(sa.corrupt_volume(v5, m, "gauss", gauss_k=k), g["a7_gaussed"]) < 1e-5
+
+
+def test_golden_model_slice(sa, golden_model):
+    """Tensors captured at the hot-path call sites of a real reference forward."""
+    g = golden_model
+    sa.CorrBlockB200.precision = "fp32"
+    try:
+        sv32 = sa.CorrBlockB200.corr(G(g["stereo_fl"]), G(g["stereo_fr"]))
+    finally:
+        sa.CorrBlockB200.precision = "tf32"
+    assert normwise(sv32, g["stereo_vol"]) < 2e-6
+    sv = sa.CorrBlockB200.corr(G(g["stereo_fl"]), G(g["stereo_fr"]))  # tensor-core path
+    assert normwise(sv, g["stereo_vol"]) < 1e-3
+    mv = 1.73 * sa.CorrBlockB200.corr(G(g["mono_nl"]), G(g["mono_nr"]))
+    assert normwise(mv, g["mono_vol"]) < 2e-6
+    blk_s = sa.CorrBlockB200(G(g["stereo_ctor"]), radius=4, num_levels=4)
+    blk_m = sa.CorrBlockB200(G(g["mono_ctor"]), radius=4, num_levels=4)
+    for it in range(int(g["iters"])):
+        c = G(g[f"it{it}_coords"])
+        s_want, m_want = g[f"it{it}_stereo"], g[f"it{it}_mono"]
+        assert maxabs(blk_s(c), s_want) < 3e-5 * max(1.0, np.abs(s_want).max())
+        assert maxabs(blk_m(c), m_want) < 3e-5 * max(1.0, np.abs(m_want).max())
+        pa, pb = sa.CorrBlockB200.lookup_pair(blk_s, blk_m, c)
+        assert torch.equal(pa, blk_s(c)) and torch.equal(pb, blk_m(c))
+
+
+# ------------------------------------------------------------------------------------------ oracle, seeded
+
+@pytest.mark.parametrize("shape", [(1, 64, 24, 128), (2, 256, 5, 312), (1, 128, 3, 168), (1, 32, 2, 40)])
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_corr_vs_oracle(sa, shape, precision):
+    b, c, h, w = shape
+    gen = torch.Generator().manual_seed(b * 1000 + c + w)
+    fl = torch.randn(b, c, h, w, generator=gen)
+    fr = torch.randn(b, c, h, w, generator=gen)
+    ref = O.aten_corr_volume(fl, fr)
+    sa.CorrBlockB200.precision = precision
+    try:
+        got = sa.CorrBlockB200.corr(fl.to(DEV), fr.to(DEV))
+    finally:
+        sa.CorrBlockB200.precision = "tf32"
+    assert got.shape == ref.shape
+    err = normwise(got, ref)
+    assert err < (1e-3 if precision == "tf32" else 2e-6), err
+
+
+def test_corr_rectangular_and_odd_fp32(sa):
+    gen = torch.Generator().manual_seed(5)
+    fl = torch.randn(2, 19, 3, 37, generator=gen)
+    fr = torch.randn(2, 19, 3, 53, generator=gen)
+    ref = O.aten_corr_volume(fl, fr)
+    got = sa.CorrBlockB200.corr(fl.to(DEV), fr.to(DEV))  # C % 8 != 0 -> SIMT kernel
+    assert got.shape == (2, 3, 37, 1, 53)
+    assert normwise(got, ref) < 2e-6
+
+
+@pytest.mark.parametrize("b,h,w", [(1, 96, 128), (2, 16, 312), (1, 8, 168), (1, 4, 240), (1, 3, 100), (1, 2, 77)])
+def test_block_vs_oracle_seeded(sa, b, h, w):
+    """Constructor + call against the ATen restatement, model-like and awkward widths."""
+    gen = torch.Generator().manual_seed(w)
+    vol = torch.randn(b, h, w, 1, w, generator=gen)
+    ref_blk = O.OracleCorrBlock(vol, num_levels=4, radius=4)
+    blk = sa.CorrBlockB200(vol.to(DEV), num_levels=4, radius=4)
+    for i, p in enumerate(blk.corr_pyramid):
+        assert np.array_equal(p.cpu().numpy(), ref_blk.corr_pyramid[i].numpy())
+    for kind in ("left", "right"):
+        coords = make_coords(b, h, w, gen, kind)
+        want = ref_blk(coords)
+        got = blk(coords.to(DEV))
+        assert got.shape == want.shape
+        assert maxabs(got, want) < 3e-5
+
+
+def test_lookup_pair_equals_two_calls(sa):
+    gen = torch.Generator().manual_seed(11)
+    b, h, w = 2, 12, 312
+    va = torch.randn(b, h, w, 1, w, generator=gen).to(DEV)
+    vb = torch.randn(b, h, w, 1, w, generator=gen).to(DEV)
+    ba, bb = sa.CorrBlockB200(va), sa.CorrBlockB200(vb)
+    coords = make_coords(b, h, w, gen).to(DEV)
+    oa, ob = sa.CorrBlockB200.lookup_pair(ba, bb, coords)
+    assert torch.equal(oa, ba(coords)) and torch.equal(ob, bb(coords))
+
+
+def test_edge_cases(sa):
+    gen = torch.Generator().manual_seed(3)
+    # single pixel row / tiny widths / W not multiple of 4 -> generic kernels
+    for (b, h, w1, w3) in [(1, 1, 1, 16), (1, 1, 9, 9), (3, 2, 17, 8)]:
+        vol = torch.randn(b, h, w1, 1, w3, generator=gen)
+        ref = O.OracleCorrBlock(vol, num_levels=3, radius=2)
+        blk = sa.CorrBlockB200(vol.to(DEV), num_levels=3, radius=2)
+        x = (torch.rand(b, 1, h, w1, generator=gen) * (w3 + 8) - 4)
+        coords = torch.cat([x, torch.zeros_like(x)], 1)
+        assert maxabs(blk(coords.to(DEV)), ref(coords)) < 3e-5
+    # coordinates far outside / non-finite magnitude: every tap is zero
+    vol = torch.randn(1, 2, 8, 1, 8, generator=gen).to(DEV)
+    blk = sa.CorrBlockB200(vol, num_levels=2, radius=4)
+    far = torch.full((1, 2, 2, 8), 1e9, device=DEV)
+    assert float(blk(far).abs().max()) == 0.0
+    assert float(blk(-far).abs().max()) == 0.0
+    # fp16 coords come back as fp16 (reference casts to coords.dtype, corr.py:115)
+    c16 = torch.zeros(1, 2, 2, 8, device=DEV, dtype=torch.float16)
+    assert blk(c16).dtype == torch.float16
+    # non-contiguous volume is accepted
+    v2 = torch.randn(1, 2, 8, 8, 1, generator=gen).to(DEV).permute(0, 1, 2, 4, 3)
+    assert sa.CorrBlockB200(v2).fullcorr.shape == (1, 2, 8, 1, 8)
+    # errors surface as exceptions
+    with pytest.raises(ValueError):
+        sa.CorrBlockB200(torch.zeros(2, 8, 8, device=DEV))
+    with pytest.raises((ValueError, RuntimeError)):
+        blk(torch.zeros(1, 2, 3, 8, device=DEV))  # wrong H
+
+
+# ------------------------------------------------------------------------------------------ full size, properties
+
+@pytest.mark.parametrize("cfg", ["c1", "c2"])
+def test_full_size_properties(sa, cfg):
+    """BASELINE configs at full size through size-independent properties (the oracle would take
+    minutes here): (1) integer coords + tap k=0 at level 0 gathers the volume itself; (2) the
+    lookup is linear in the volume; (3) a constant volume looks up to a constant inside the
+    image; (4) pyramid levels are exact means of level 0; (5) TF32 corr matches an fp64 dot
+    product on sampled entries."""
+    b, c, h, w = {"c1": (1, 256, 96, 128), "c2": (8, 256, 96, 312)}[cfg]
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    fl = torch.randn(b, c, h, w, device=DEV, generator=gen)
+    fr = torch.randn(b, c, h, w, device=DEV, generator=gen)
+    vol = sa.CorrBlockB200.corr(fl, fr)
+    assert vol.shape == (b, h, w, 1, w)
+    # (5) sampled entries against float64
+    idx = torch.randint(0, b * h * w * w, (4096,), device=DEV, generator=gen)
+    bb = idx // (h * w * w)
+    hh = (idx // (w * w)) % h
+    w2 = (idx // w) % w
+    w3 = idx % w
+    ref = (fl[bb, :, hh, w2].double() * fr[bb, :, hh, w3].double()).sum(1) / 16.0
+    got = vol.view(-1)[idx].double()
+    assert float((got - ref).abs().max() / vol.abs().max()) < 1e-3
+    blk = sa.CorrBlockB200(vol, num_levels=4, radius=4)
+    # (4) pyramid
+    v4 = vol.view(b * h * w, w)
+    l1 = 0.5 * (v4[:, 0::2] + v4[:, 1::2])
+    assert torch.equal(blk.corr_pyramid[1].view(b * h * w, -1), l1)
+    l2 = 0.5 * (l1[:, 0::2] + l1[:, 1::2])
+    assert torch.equal(blk.corr_pyramid[2].view(b * h * w, -1), l2)
+    l3 = 0.5 * (l2[:, 0 : 2 * (l2.shape[1] // 2) : 2] + l2[:, 1 : 2 * (l2.shape[1] // 2) : 2])
+    assert torch.equal(blk.corr_pyramid[3].view(b * h * w, -1), l3)
+    # (1) gather
+    tgt = torch.randint(0, w, (b, 1, h, w), device=DEV, generator=gen).float()
+    coords = torch.cat([tgt, torch.zeros_like(tgt)], 1)
+    out = blk(coords)
+    want = torch.gather(vol.view(b, h, w, w), 3, tgt.view(b, h, w, 1).long()).view(b, h, w)
+    assert torch.equal(out[:, 4], want)
+    # (2) linearity
+    coords = torch.cat([tgt - torch.rand(b, 1, h, w, device=DEV, generator=gen) * 40, torch.zeros_like(tgt)], 1)
+    o1 = blk(coords)
+    blk2 = sa.CorrBlockB200(vol * 2.0 + 1.0, num_levels=4, radius=4)
+    ones = sa.CorrBlockB200(torch.ones_like(vol), num_levels=4, radius=4)
+    o2 = blk2(coords)
+    assert float((o2 - (2.0 * o1 + ones(coords))).abs().max()) < 1e-4
+    # (3) constant volume: taps fully inside the row read exactly 1
+    xin = torch.rand(b, 1, h, w, device=DEV, generator=gen) * (w - 80) + 40
+    oc = ones(torch.cat([xin, torch.zeros_like(xin)], 1))
+    assert float((oc[:, :9] - 1.0).abs().max()) < 1e-6

@@ -1,0 +1,81 @@
+"""Host-side checks that need no GPU: the C-ABI library loads and exports every symbol the header
+declares, the custom ops are registered for CUDA only, and argument errors surface as exceptions."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sa_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sa_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import stereoanywhere_b200._lib as L
+
+    lib = L.load()
+    names = _declared_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/sa_b200.h but not exported"
+    assert sorted(L.EXPORTS) == names
+    assert lib.sa_abi_version() == 1
+
+
+def test_library_is_in_tree_and_self_contained():
+    import stereoanywhere_b200._lib as L
+
+    assert L.LIB_PATH.startswith(ROOT) and os.path.exists(L.LIB_PATH)
+    # no torch / libcudart.so runtime dependency: plain C ABI, static cudart
+    import subprocess
+
+    deps = subprocess.run(["ldd", L.LIB_PATH], capture_output=True, text=True).stdout
+    assert "libtorch" not in deps and "libc10" not in deps
+
+
+def test_argument_errors_return_negative_codes_without_a_gpu():
+    import stereoanywhere_b200._lib as L
+
+    lib = L.load()
+    rc = lib.sa_corr_fp32(None, None, None, 1, 3, 4, 8, 8, 1.0, 1.0, None)
+    assert rc == -1 and b"null" in lib.sa_last_error()
+    rc = lib.sa_pyramid(None, 0, 8, 8, 1, None, None, None, 0, 0, 0, None, None, 0.0, 0, None, None)
+    assert rc == -1
+    rc = lib.sa_lookup(None, None, None, 4, 4, None, 0, None, 1, 1, 8, 0, 0, None)
+    assert rc == -1
+    with pytest.raises(L.SaError):
+        L.check(rc, "sa_lookup")
+
+
+def test_ops_registered_cuda_only():
+    import stereoanywhere_b200 as sa
+
+    for name in sa.ops.OP_NAMES:
+        assert hasattr(torch.ops.sa_b200, name)
+    f = torch.zeros(1, 8, 2, 8)
+    with pytest.raises(NotImplementedError):
+        sa.CorrBlockB200.corr(f, f)  # CPU tensors: no kernel registered, no fallback
+    with pytest.raises(NotImplementedError):
+        sa.CorrBlockB200(torch.zeros(1, 2, 8, 1, 8))
+
+
+def test_level_geometry():
+    from stereoanywhere_b200 import ops
+
+    assert ops.level_widths(312, 4) == [312, 156, 78, 39]
+    assert ops.level_widths(39, 4) == [39, 19, 9, 4]
+    assert [ops.level_pitch(w) for w in (312, 156, 78, 39)] == [312, 156, 80, 40]
+
+
+def test_requires_grad_is_rejected():
+    import stereoanywhere_b200 as sa
+
+    v = torch.zeros(1, 2, 8, 1, 8, requires_grad=True)
+    with pytest.raises(NotImplementedError):
+        sa.CorrBlockB200(v)

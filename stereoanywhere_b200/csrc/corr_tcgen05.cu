@@ -1,6 +1,371 @@
-// placeholder until the tcgen05 kernel lands (replaced in the next commit)
+// A1 - stereo correlation volume on the 5th-gen tensor cores
+// (reference: models/stereoanywhere/corr.py:117-132, torch.einsum('aijk,aijh->ajkh') / sqrt(C)).
+//
+// Per image row (b,h):  V[w2,w3] = sum_c L[b,c,h,w2] R[b,c,h,w3].  Both operands are W-contiguous in
+// NCHW, i.e. "MN-major" for the MMA: a 4-D TMA tensor map {W,H,C,B} with box {32,1,BK,1} and the
+// 128-byte swizzle drops a [BK channels][32 columns] slab straight into shared memory in the
+// canonical UMMA MN-major SWIZZLE_128B (32-byte atom) layout - no transpose, no conversion pass; the fp32 bits
+// are consumed as TF32 by tcgen05.mma.kind::tf32 with an fp32 accumulator in TMEM.
+//
+// One CTA = one [128 x BN<=256] output tile (TMEM: 256 columns, so two CTAs share an SM and one
+// CTA's epilogue overlaps the other's loads/MMAs).
+//   warp 0 / lane 0 : TMA producer (mbarrier full/empty ring, BK = 32 channels per stage)
+//   warp 1 / lane 0 : tcgen05.mma issuer, tcgen05.commit frees the stage / publishes the accumulator
+//   all 4 warps     : epilogue - tcgen05.ld (lane = output row), scale, swizzled st.shared,
+//                     TMA store of [128 x 32] boxes (rows / columns outside the image are clipped
+//                     by the 3-D output tensor map {W3, W2, B*H}).
+// HBM-bound by the fp32 volume write (AI ~ 36 flop/B at C=256, W=312); the tensor pipe idles ~2/3.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "sa_common.cuh"
-extern "C" int sa_corr_tf32(const float*, const float*, float*, int, int, int, int, int, float, float, const float*,
-                            const float*, double, float*, float*, float*, int64_t, int64_t, int64_t, void*) {
-  SA_FAIL(SA_E_UNSUPPORTED, "sa_corr_tf32: not built yet");
+
+namespace sa {
+
+constexpr int kBM = 128;       // rows of the accumulator tile (w2)
+constexpr int kBK = 32;        // channels per pipeline stage (4 UMMA k-steps of 8)
+constexpr int kBox = 32;       // fp32 columns per TMA box = 128 B = one swizzle row
+constexpr int kBoxBytes = kBox * kBK * 4;  // 4096
+constexpr int kTmemCols = 256;
+constexpr int kMaxStages = 4;
+constexpr int kStageBudget = 106 * 1024;   // two CTAs per SM
+
+// ---- PTX helpers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  printf("sa_corr_tf32: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// SM100 shared-memory matrix descriptor for an MN-major 32-bit (TF32) operand.  The only layout the
+// tensor core accepts for that case is SWIZZLE_128B with 32-byte atomicity (layout_type 1; the
+// TMA twin is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of 32 columns (128 B), the four 32-byte
+// chunks of a row XOR-ed with (row & 3), atoms of 4 channel rows (512 B).
+//   start address >> 4 | LBO >> 4 at bit 16 (stride between 32-column groups) |
+//   SBO >> 4 at bit 32 (stride between 4-channel atoms) | version 1 at bit 46 | layout at bit 61.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+struct CorrTcArgs {
+  int C, H, W2, W3;
+  int m_tiles, n_tiles, BN;  // BN: accumulator columns per tile (multiple of 32, <= 256)
+  int nstage;
+  float divisor, post_scale;
+  int debug;  // bring-up only (SA_B200_TC_DEBUG): 1 = store a constant, 2 = store operand A channel 0
+};
+
+__global__ void __launch_bounds__(128)
+corr_tf32_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constant__ CUtensorMap map_r,
+                 const __grid_constant__ CUtensorMap map_o, const CorrTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  // stages first (1024-byte aligned for the 128B swizzle), barriers after
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int n_boxes_b = a.BN / kBox;
+  const uint32_t stage_bytes = (uint32_t)(kBM / kBox + n_boxes_b) * kBoxBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)a.nstage * stage_bytes);
+  uint64_t* full = bars;                    // [nstage]
+  uint64_t* empty = bars + kMaxStages;      // [nstage]
+  uint64_t* accum = bars + 2 * kMaxStages;  // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int tile = blockIdx.x;
+  const int tn = tile % a.n_tiles;
+  tile /= a.n_tiles;
+  const int tm = tile % a.m_tiles;
+  const int bh = tile / a.m_tiles;
+  const int b = bh / a.H, h = bh % a.H;
+  const int m0 = tm * kBM, n0 = tn * a.BN;
+  const int kchunks = a.C / kBK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.nstage; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_l) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_r) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_o) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  // boxes that lie wholly outside the image are neither loaded nor waited for: their rows / columns
+  // of the accumulator are clipped by the output tensor map
+  int a_boxes = 0, b_boxes = 0;
+  for (int g = 0; g < kBM / kBox; ++g) a_boxes += (m0 + g * kBox < a.W2);
+  for (int g = 0; g < n_boxes_b; ++g) b_boxes += (n0 + g * kBox < a.W3);
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    for (int kc = 0; kc < kchunks; ++kc) {
+      const int s = kc % a.nstage;
+      const uint32_t ph = (uint32_t)(kc / a.nstage) & 1u;
+      mbar_wait(&empty[s], ph ^ 1u);
+      mbar_expect_tx(&full[s], (uint32_t)(a_boxes + b_boxes) * kBoxBytes);
+      uint8_t* sa_ = base + (size_t)s * stage_bytes;
+      uint8_t* sb_ = sa_ + (kBM / kBox) * kBoxBytes;
+      for (int g = 0; g < a_boxes; ++g) tma_load_4d(sa_ + g * kBoxBytes, &map_l, &full[s], m0 + g * kBox, h, kc * kBK, b);
+      for (int g = 0; g < b_boxes; ++g) tma_load_4d(sb_ + g * kBoxBytes, &map_r, &full[s], n0 + g * kBox, h, kc * kBK, b);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    // instruction descriptor: D=f32, A=B=tf32, both MN-major, N = BN, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    for (int kc = 0; kc < kchunks; ++kc) {
+      const int s = kc % a.nstage;
+      const uint32_t ph = (uint32_t)(kc / a.nstage) & 1u;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      const uint32_t sa_ = smem_u32(base + (size_t)s * stage_bytes);
+      const uint32_t sb_ = sa_ + (kBM / kBox) * kBoxBytes;
+#pragma unroll
+      for (int k = 0; k < kBK / 8; ++k) {
+        const uint64_t ad = make_desc(sa_ + k * 1024, kBoxBytes, 512);
+        const uint64_t bd = make_desc(sb_ + k * 1024, kBoxBytes, 512);
+        umma_tf32(tmem_acc, ad, bd, idesc, (uint32_t)((kc | k) != 0));
+      }
+      umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
+    }
+    umma_commit(accum);        // accumulator complete
+  }
+
+  // ---------------------------------------------------------------------- epilogue (all warps)
+  mbar_wait(accum, 0);
+  tc_fence_after();
+  __syncwarp();
+  uint8_t* stag = base;  // the pipeline stages are dead now: 2 x [128 rows][128 B] staging tiles
+  const int row = tid;   // accumulator lane = output row m0 + row
+  float dbg_a = 0.f;
+  if (a.debug == 2) {    // element (m = row, k = 0) of the A slab left in stage 0
+    dbg_a = *reinterpret_cast<const float*>(base + (row >> 5) * kBoxBytes + ((((row & 31) >> 2) ^ 0) << 4) + (row & 3) * 4);
+    __syncthreads();
+  }
+  const uint32_t t_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
+  const int nchunks = (min(a.BN, a.W3 - n0) + kBox - 1) / kBox;
+  for (int c = 0; c < nchunks; ++c) {
+    uint32_t v[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(t_lane + (uint32_t)(c * kBox)));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (a.debug == 2) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(dbg_a * a.divisor);
+    }
+    if (a.debug == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __float_as_uint((float)(c * 32 + i) * a.divisor);
+    }
+    uint8_t* tile_s = stag + (c & 1) * (kBM * 128);
+    if (c >= 2) {  // the store issued two chunks ago has to be done reading this buffer
+      if (tid == 0) tma_wait_read<1>();
+      __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 o;
+      o.x = __fdiv_rn(__uint_as_float(v[4 * j + 0]), a.divisor) * a.post_scale;
+      o.y = __fdiv_rn(__uint_as_float(v[4 * j + 1]), a.divisor) * a.post_scale;
+      o.z = __fdiv_rn(__uint_as_float(v[4 * j + 2]), a.divisor) * a.post_scale;
+      o.w = __fdiv_rn(__uint_as_float(v[4 * j + 3]), a.divisor) * a.post_scale;
+      *reinterpret_cast<float4*>(tile_s + row * 128 + ((j ^ (row & 7)) << 4)) = o;  // 128B swizzle
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      tma_store_3d(&map_o, tile_s, n0 + c * kBox, m0, bh);
+      tma_commit();
+    }
+  }
+  if (tid == 0) tma_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)kTmemCols)
+                 : "memory");
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                    const cuuint32_t* box, CUtensorMapSwizzle swz, const char* what) {
+  EncodeTiledFn fn = encode_fn();
+  SA_REQUIRE(fn != nullptr, SA_E_UNSUPPORTED, "sa_corr_tf32: cuTensorMapEncodeTiled unavailable (no driver?)");
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  // bring-up switch: SA_B200_TMA_TF32=1 loads the operands as TFLOAT32 (TMA-side conversion)
+  static const bool tf32_type = getenv("SA_B200_TMA_TF32") && atoi(getenv("SA_B200_TMA_TF32")) != 0;
+  const CUtensorMapDataType dt = (tf32_type && swz == CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                                     ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
+                  ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SA_REQUIRE(r == CUDA_SUCCESS, SA_E_INVALID, "sa_corr_tf32: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what,
+             (int)r);
+  return 0;
+}
+
+}  // namespace sa
+
+extern "C" int sa_corr_tf32(const float* fmap_l, const float* fmap_r, float* vol, int B, int C, int H, int W2, int W3,
+                            float divisor, float post_scale, const float* trunc_disp, const float* trunc_conf,
+                            double trunc_gain, float* pyr1, float* pyr2, float* pyr3, int64_t pitch1, int64_t pitch2,
+                            int64_t pitch3, void* stream) {
+  using namespace sa;
+  (void)trunc_gain; (void)pitch1; (void)pitch2; (void)pitch3;
+  SA_REQUIRE(fmap_l && fmap_r && vol, SA_E_INVALID, "sa_corr_tf32: null pointer");
+  SA_REQUIRE(B > 0 && C > 0 && H > 0 && W2 > 0 && W3 > 0, SA_E_INVALID, "sa_corr_tf32: sizes must be positive");
+  SA_REQUIRE(divisor != 0.f, SA_E_INVALID, "sa_corr_tf32: divisor == 0");
+  SA_REQUIRE(C % kBK == 0, SA_E_UNSUPPORTED, "sa_corr_tf32: C must be a multiple of %d (got %d)", kBK, C);
+  SA_REQUIRE(W2 % 4 == 0 && W3 % 4 == 0, SA_E_UNSUPPORTED, "sa_corr_tf32: W2 and W3 must be multiples of 4");
+  SA_REQUIRE(aligned16(fmap_l) && aligned16(fmap_r) && aligned16(vol), SA_E_ALIGN,
+             "sa_corr_tf32: pointers must be 16-byte aligned");
+  SA_REQUIRE(!trunc_disp && !trunc_conf && !pyr1 && !pyr2 && !pyr3, SA_E_UNSUPPORTED,
+             "sa_corr_tf32: fused truncation / pyramid epilogue is not available in this build");
+
+  CorrTcArgs a = {};
+  a.C = C; a.H = H; a.W2 = W2; a.W3 = W3;
+  a.divisor = divisor; a.post_scale = post_scale;
+  {
+    const char* e = getenv("SA_B200_TC_DEBUG");
+    a.debug = e ? atoi(e) : 0;
+  }
+  a.m_tiles = (W2 + kBM - 1) / kBM;
+  a.n_tiles = (W3 + 255) / 256;
+  const int per = (W3 + a.n_tiles - 1) / a.n_tiles;
+  a.BN = (per + kBox - 1) / kBox * kBox;  // multiple of 32 (hence of 16: legal UMMA N for M = 128)
+  const int stage_bytes = (kBM / kBox + a.BN / kBox) * kBoxBytes;
+  a.nstage = kStageBudget / stage_bytes;
+  if (a.nstage > kMaxStages) a.nstage = kMaxStages;
+  if (a.nstage > C / kBK) a.nstage = C / kBK;
+  SA_REQUIRE(a.nstage >= 1, SA_E_UNSUPPORTED, "sa_corr_tf32: tile does not fit shared memory");
+  const long long tiles = (long long)B * H * a.m_tiles * a.n_tiles;
+  SA_REQUIRE(tiles < (1ll << 31), SA_E_UNSUPPORTED, "sa_corr_tf32: too many tiles");
+
+  CUtensorMap ml, mr, mo;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)W2, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)W2 * 4, (cuuint64_t)H * W2 * 4, (cuuint64_t)C * H * W2 * 4};
+    cuuint32_t box[4] = {kBox, 1, kBK, 1};
+    int rc = make_map(&ml, fmap_l, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, "fmap_l");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)W3, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+    cuuint64_t str[3] = {(cuuint64_t)W3 * 4, (cuuint64_t)H * W3 * 4, (cuuint64_t)C * H * W3 * 4};
+    cuuint32_t box[4] = {kBox, 1, kBK, 1};
+    int rc = make_map(&mr, fmap_r, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, "fmap_r");
+    if (rc) return rc;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)W3, (cuuint64_t)W2, (cuuint64_t)B * H};
+    cuuint64_t str[2] = {(cuuint64_t)W3 * 4, (cuuint64_t)W2 * W3 * 4};
+    cuuint32_t box[3] = {kBox, kBM, 1};
+    int rc = make_map(&mo, vol, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "vol");
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + (size_t)a.nstage * stage_bytes + (2 * kMaxStages + 2) * sizeof(uint64_t);
+  static thread_local size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(corr_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) SA_FAIL((int)e, "sa_corr_tf32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    configured = smem;
+  }
+  corr_tf32_kernel<<<(unsigned)tiles, 128, smem, (cudaStream_t)stream>>>(ml, mr, mo, a);
+  return finish_launch("sa_corr_tf32");
 }

@@ -35,8 +35,9 @@ __global__ void __launch_bounds__(THREADS) lookup_vec_kernel(const LookupArgs a)
   constexpr int NC = NL * NT;      // output channels per volume
   constexpr int SP = TILE + 4;     // smem pitch: keeps rows 16 B aligned, spreads channels over banks
   constexpr int GROUPS = THREADS / 4;
-  constexpr int ITEMS = NV * NL * TILE;
+  constexpr int ITEMS = NL * TILE;             // (level, pixel) windows per volume
   static_assert(ITEMS % GROUPS == 0, "uniform trip count (shuffles inside the loop)");
+  constexpr int PER = ITEMS / GROUPS;          // windows per 4-lane group and volume
   static_assert(2 * R + 4 <= 15, "window + misalignment must fit four 16-byte chunks");
 
   extern __shared__ __align__(16) float smem[];
@@ -56,36 +57,49 @@ __global__ void __launch_bounds__(THREADS) lookup_vec_kernel(const LookupArgs a)
   const int j = tid & 3;
   const long long row0 = (long long)b * a.HW + hw0;
 
-#pragma unroll 4
-  for (int item = grp; item < ITEMS; item += GROUPS) {
-    const int t = item % TILE;
-    const int vi = item / TILE;
-    const int i = vi % NL;
-    const int v = vi / NL;
-
-    const float xs = s_x[t] * __int_as_float((127 - i) << 23);  // x / 2^i, exact
-    float fl = floorf(xs);
-    const float f = xs - fl;
-    fl = fminf(fmaxf(fl, -1.0e6f), 1.0e6f);  // far-away / inf coords: every tap lands outside
-    const int start = (int)fl - R;
-    const int o = start & 3;
-    const int e0 = ((start >> 2) + j) << 2;   // first column of this lane's 16-byte chunk
-    const int wi = a.width[i];
-    const bool ok = (t < npx) && (e0 >= 0) && (e0 < wi);
-    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ok) q = ld_stream_v4(a.lvl[v][i] + (row0 + t) * a.pitch[v][i] + e0);
-    if (e0 + 1 >= wi) q.y = 0.f;  // row padding / right border
-    if (e0 + 2 >= wi) q.z = 0.f;
-    if (e0 + 3 >= wi) q.w = 0.f;
-    const float nx = __shfl_down_sync(0xffffffffu, q.x, 1);
-
-    const float g = 1.0f - f;
-    const int kb = 4 * j - o;  // tap index of q.x
-    float* so = s_out + ((v * NL + i) * NT) * SP + t;
-    if ((unsigned)(kb + 0) < (unsigned)NT) so[(kb + 0) * SP] = g * q.x + f * q.y;
-    if ((unsigned)(kb + 1) < (unsigned)NT) so[(kb + 1) * SP] = g * q.y + f * q.z;
-    if ((unsigned)(kb + 2) < (unsigned)NT) so[(kb + 2) * SP] = g * q.z + f * q.w;
-    if ((unsigned)(kb + 3) < (unsigned)NT) so[(kb + 3) * SP] = g * q.w + f * nx;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    // ---- issue every load of this volume before touching any result: PER independent 128-bit
+    //      requests in flight per lane (the gather is latency-bound otherwise)
+    float4 q[PER];
+    float fr[PER];
+    int kb[PER];
+#pragma unroll
+    for (int n = 0; n < PER; ++n) {
+      const int item = grp + n * GROUPS;
+      const int t = item % TILE;
+      const int i = item / TILE;
+      const float xs = s_x[t] * __int_as_float((127 - i) << 23);  // x / 2^i, exact
+      float fl = floorf(xs);
+      fr[n] = xs - fl;
+      fl = fminf(fmaxf(fl, -1.0e6f), 1.0e6f);  // far-away / inf coords: every tap lands outside
+      const int start = (int)fl - R;
+      const int o = start & 3;
+      kb[n] = 4 * j - o;                        // tap index of this lane's first element
+      const int e0 = ((start >> 2) + j) << 2;   // first column of this lane's 16-byte chunk
+      const int wi = a.width[i];
+      // chunk needed iff it holds one of the 2R+2 window elements and lies inside the row
+      const bool ok = (t < npx) && (e0 >= 0) && (e0 < wi) && (4 * j <= o + 2 * R + 1);
+      q[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) q[n] = ld_stream_v4(a.lvl[v][i] + (row0 + t) * a.pitch[v][i] + e0);
+      if (e0 + 1 >= wi) q[n].y = 0.f;  // row padding / right border
+      if (e0 + 2 >= wi) q[n].z = 0.f;
+      if (e0 + 3 >= wi) q[n].w = 0.f;
+    }
+#pragma unroll
+    for (int n = 0; n < PER; ++n) {
+      const int item = grp + n * GROUPS;
+      const int t = item % TILE;
+      const int i = item / TILE;
+      const float nx = __shfl_down_sync(0xffffffffu, q[n].x, 1);
+      const float f = fr[n], g = 1.0f - fr[n];
+      float* so = s_out + ((v * NL + i) * NT) * SP + t;
+      const int k0 = kb[n];
+      if ((unsigned)(k0 + 0) < (unsigned)NT) so[(k0 + 0) * SP] = g * q[n].x + f * q[n].y;
+      if ((unsigned)(k0 + 1) < (unsigned)NT) so[(k0 + 1) * SP] = g * q[n].y + f * q[n].z;
+      if ((unsigned)(k0 + 2) < (unsigned)NT) so[(k0 + 2) * SP] = g * q[n].z + f * q[n].w;
+      if ((unsigned)(k0 + 3) < (unsigned)NT) so[(k0 + 3) * SP] = g * q[n].w + f * nx;
+    }
   }
   __syncthreads();
 
@@ -198,6 +212,7 @@ static int lookup_common(LookupArgs& a, int B, int H, int W, cudaStream_t st) {
       vec = vec && aligned16(a.lvl[v][i]) && (a.pitch[v][i] % 4 == 0);
     }
   for (int v = 0; v < NV; ++v) vec = vec && aligned16(a.out[v]);
+  (void)num_sms();  // also applies the process-wide device limits once
   a.HW = H * W;
   a.W = W;
   a.xoff = (float)a.pad0;

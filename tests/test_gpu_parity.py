@@ -208,12 +208,18 @@ def test_block_vs_oracle_seeded(sa, b, h, w):
     blk = sa.CorrBlockB200(vol.to(DEV), num_levels=4, radius=4)
     for i, p in enumerate(blk.corr_pyramid):
         assert np.array_equal(p.cpu().numpy(), ref_blk.corr_pyramid[i].numpy())
+    levels64 = O.closed_pyramid(vol[:, :, :, 0].numpy(), 4)
     for kind in ("left", "right"):
         coords = make_coords(b, h, w, gen, kind)
         want = ref_blk(coords)
         got = blk(coords.to(DEV))
         assert got.shape == want.shape
-        assert maxabs(got, want) < 3e-5
+        # float64 closed form on the same fp32 coords: only our own fp32 blend error remains
+        assert maxabs(got, O.closed_lookup(levels64, coords[:, 0].numpy(), radius=4)) < 5e-6
+        # ATen reference: grid_sample's normalise / un-normalise round trip perturbs the sample
+        # position by ~4 eps W/2 px; on N(0,1) rows (tap-to-tap differences up to ~8) that is
+        # ~2e-6 W absolute (6e-4 at W=312) of *reference* noise
+        assert maxabs(got, want) < 2e-6 * max(w, 16)
 
 
 def test_lookup_pair_equals_two_calls(sa):

@@ -103,6 +103,25 @@ int sa_lookup2(const float* const* h_levels_a, const float* const* h_levels_b, c
                const float* coords, int64_t coords_bstride, float* out_a, float* out_b, int B, int H, int W,
                void* stream);
 
+/* ---------------------------------------------------------------- A3 + A4, line-packed (fast path)
+ * For num_levels == 4, radius == 4, W3 % 8 == 0 (the model's configuration) the pyramid can be
+ * stored "line-packed": per volume row and per block of 8 level-0 columns ONE 128-byte line that
+ * holds every value a lookup with floor(x) in that block needs (see csrc/packed.cu).  HBM serves
+ * L2 misses in whole 128-byte lines, so a lookup costs 1 line per (pixel, volume) instead of >= 4.
+ * Results are bit-identical to sa_pyramid + sa_lookup.
+ *   sa_packed_row_floats(W3)  floats per volume row of the packed array ((W3/8 + 9) * 32)
+ *   sa_pack_pyramid           src: rows x W3 fp32 -> packed: rows x sa_packed_row_floats(W3);
+ *                             optional truncation as in sa_pyramid (the masked level 0 is not
+ *                             materialised)
+ *   sa_lookup_packed          `CorrBlock1D.__call__` for one (packed_b == out_b == NULL) or two
+ *                             volumes; coords / out as in sa_lookup, pad = 0.
+ */
+int64_t sa_packed_row_floats(int W3);
+int sa_pack_pyramid(const float* src, int64_t rows, int W3, const float* trunc_disp, const float* trunc_conf,
+                    double trunc_gain, int w2_size, float* packed, void* stream);
+int sa_lookup_packed(const float* packed_a, const float* packed_b, int W3, const float* coords,
+                     int64_t coords_bstride, float* out_a, float* out_b, int B, int H, int W, void* stream);
+
 /* ---------------------------------------------------------------- A5: truncation mask (standalone)
  * mask[b,h,w2,w3] = (1-c) + c * (sigmoid((w2 - d) - w3) * (1-g) + g); writes `out` = mask * vol
  * when vol != NULL, else the mask itself.  Replaces `truncate_corr_volume_v2`

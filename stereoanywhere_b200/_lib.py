@@ -37,6 +37,12 @@ def _declare(lib):
     lib.sa_lookup2.restype = i
     lib.sa_lookup2.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(i), C.POINTER(i64), C.POINTER(i64), i, i,
                                vp, i64, vp, vp, i, i, i, vp]
+    lib.sa_packed_row_floats.restype = i64
+    lib.sa_packed_row_floats.argtypes = [i]
+    lib.sa_pack_pyramid.restype = i
+    lib.sa_pack_pyramid.argtypes = [vp, i64, i, vp, vp, d, i, vp, vp]
+    lib.sa_lookup_packed.restype = i
+    lib.sa_lookup_packed.argtypes = [vp, vp, i, vp, i64, vp, vp, i, i, i, vp]
     lib.sa_truncate.restype = i
     lib.sa_truncate.argtypes = [vp, vp, vp, d, vp, i64, i, i, vp]
     lib.sa_masked_volume.restype = i
@@ -47,7 +53,7 @@ def _declare(lib):
 
 EXPORTS = [
     "sa_abi_version", "sa_last_error", "sa_corr_fp32", "sa_corr_tf32", "sa_pyramid", "sa_lookup", "sa_lookup2",
-    "sa_truncate", "sa_masked_volume", "sa_corrupt",
+    "sa_truncate", "sa_masked_volume", "sa_corrupt", "sa_packed_row_floats", "sa_pack_pyramid", "sa_lookup_packed",
 ]
 
 
@@ -66,8 +72,18 @@ def load():
                 f"stereoanywhere_b200: CUDA library {LIB_PATH} is missing and could not be built ({e}). "
                 "There is no CPU fallback; run `python -m stereoanywhere_b200.build`."
             ) from e
-    lib = C.CDLL(LIB_PATH)
-    _declare(lib)
+    try:
+        lib = C.CDLL(LIB_PATH)
+        _declare(lib)
+    except (OSError, AttributeError) as stale:  # .so older than this binding: rebuild once
+        from . import build as _build
+
+        try:
+            _build.build(force=True)
+        except Exception as e:
+            raise SaError(f"stereoanywhere_b200: {LIB_PATH} is stale ({stale}) and could not be rebuilt ({e})") from e
+        lib = C.CDLL(LIB_PATH)
+        _declare(lib)
     if lib.sa_abi_version() != 1:
         raise SaError("stereoanywhere_b200: ABI version mismatch between _lib.py and libsa_b200.so")
     _lib = lib

@@ -57,30 +57,57 @@ class CorrBlockB200:
         b, h, w2, _, w3 = fullcorr.shape
         if not fullcorr.is_contiguous():
             fullcorr = fullcorr.contiguous()
-        rows = fullcorr.view(b * h * w2, w3)
-        if truncate is not None:
-            disp, conf, gain = truncate
-            levels = _OPS.pyramid(rows, num_levels, disp, conf, float(gain))
-            self.fullcorr = levels[0].view(b, h, w2, 1, w3)
-        else:
-            levels = _OPS.pyramid(rows, num_levels, None, None, 0.0)
-            self.fullcorr = fullcorr
-        self._levels: List[torch.Tensor] = list(levels)
+        self._src = fullcorr            # the tensor handed in (kept alive like the reference does)
+        self._truncate = None if truncate is None else (truncate[0], truncate[1], float(truncate[2]))
+        self._shape = (b, h, w2, w3)
         self._widths: List[int] = ops.level_widths(w3, num_levels)
-        self._shape = (b, h, w2)
+        self._levels: Optional[List[torch.Tensor]] = None
+        self._packed: Optional[torch.Tensor] = None
+        rows = fullcorr.view(b * h * w2, w3)
+        if self.layout == "packed" and ops.packable(num_levels, radius, w3, self.pad):
+            # one 128-byte line per (pixel, volume) lookup; levels are materialised only on request
+            t = self._truncate
+            self._packed = _OPS.pack_pyramid(rows, t[0] if t else None, t[1] if t else None, t[2] if t else 0.0)
+        else:
+            self._build_levels()
+
+    #: "packed" (default; used whenever num_levels=4, radius=4, W3 % 8 == 0, pad=[0,0]) or "levels"
+    layout = os.environ.get("SA_B200_LAYOUT", "packed")
+
+    def _build_levels(self):
+        if self._levels is None:
+            b, h, w2, w3 = self._shape
+            rows = self._src.view(b * h * w2, w3)
+            t = self._truncate
+            self._levels = list(_OPS.pyramid(rows, self.num_levels, t[0] if t else None, t[1] if t else None,
+                                             t[2] if t else 0.0))
+        return self._levels
+
+    @property
+    def fullcorr(self) -> torch.Tensor:
+        """The volume the lookups see, `[B,H,W2,1,W3]` (reference attribute, corr.py:83).  With
+        `truncate=` this is the product T*V (formed on first access when the packed layout is in use)."""
+        if self._truncate is None:
+            return self._src
+        b, h, w2, w3 = self._shape
+        return self._build_levels()[0].view(b, h, w2, 1, w3)
 
     @property
     def corr_pyramid(self) -> List[torch.Tensor]:
         """Levels as `[B*H*W2, 1, 1, W3_i]` views like the reference attribute (corr.py:87-91).
-        (Levels >= 1 are views into 16-byte-pitched rows; the reference's dead extra level is absent.)"""
-        return [lv[:, :w].unsqueeze(1).unsqueeze(1) for lv, w in zip(self._levels, self._widths)]
+        (Levels >= 1 are views into 16-byte-pitched rows; the reference's dead extra level is absent.
+        With the packed layout they are built on first access.)"""
+        return [lv[:, :w].unsqueeze(1).unsqueeze(1) for lv, w in zip(self._build_levels(), self._widths)]
 
     def __call__(self, coords: torch.Tensor) -> torch.Tensor:
         _no_grad_check(coords)
         dt = coords.dtype
         if dt != torch.float32:
             coords = coords.float()
-        out = _OPS.lookup(self._levels, self._widths, coords, self.radius, self.pad[0], self.pad[1])
+        if self._packed is not None:
+            out = _OPS.lookup_packed(self._packed, self._shape[3], coords)
+        else:
+            out = _OPS.lookup(self._levels, self._widths, coords, self.radius, self.pad[0], self.pad[1])
         return out if dt == torch.float32 else out.to(dt)
 
     # ---- protocol: static corr --------------------------------------------------------------
@@ -112,12 +139,16 @@ class CorrBlockB200:
         """`(block_a(coords), block_b(coords))` with one launch (stereoanywhere.py:270-271)."""
         _no_grad_check(coords)
         if (block_a.radius != block_b.radius or block_a._widths != block_b._widths
-                or block_a.pad != [0, 0] or block_b.pad != [0, 0]):
+                or block_a.pad != [0, 0] or block_b.pad != [0, 0]
+                or (block_a._packed is None) != (block_b._packed is None)):
             return block_a(coords), block_b(coords)
         dt = coords.dtype
         if dt != torch.float32:
             coords = coords.float()
-        oa, ob = _OPS.lookup2(block_a._levels, block_b._levels, block_a._widths, coords, block_a.radius)
+        if block_a._packed is not None:
+            oa, ob = _OPS.lookup_packed2(block_a._packed, block_b._packed, block_a._shape[3], coords)
+        else:
+            oa, ob = _OPS.lookup2(block_a._levels, block_b._levels, block_a._widths, coords, block_a.radius)
         return (oa, ob) if dt == torch.float32 else (oa.to(dt), ob.to(dt))
 
 

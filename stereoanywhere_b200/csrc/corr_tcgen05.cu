@@ -124,7 +124,9 @@ corr_tf32_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constan
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int n_boxes_b = a.BN / kBox;
   const uint32_t stage_bytes = (uint32_t)(kBM / kBox + n_boxes_b) * kBoxBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)a.nstage * stage_bytes);
+  // the epilogue re-uses the stage area as 2 x [128 rows][128 B] staging tiles: keep it >= 32 KB
+  const uint32_t pipe_bytes = max((uint32_t)a.nstage * stage_bytes, (uint32_t)(2 * kBM * 128));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + pipe_bytes);
   uint64_t* full = bars;                    // [nstage]
   uint64_t* empty = bars + kMaxStages;      // [nstage]
   uint64_t* accum = bars + 2 * kMaxStages;  // [1]
@@ -288,8 +290,10 @@ static int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t*
   EncodeTiledFn fn = encode_fn();
   SA_REQUIRE(fn != nullptr, SA_E_UNSUPPORTED, "sa_corr_tf32: cuTensorMapEncodeTiled unavailable (no driver?)");
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  // bring-up switch: SA_B200_TMA_TF32=1 loads the operands as TFLOAT32 (TMA-side conversion)
-  static const bool tf32_type = getenv("SA_B200_TMA_TF32") && atoi(getenv("SA_B200_TMA_TF32")) != 0;
+  // Operands are declared TFLOAT32 to the TMA unit: it rounds fp32 -> tf32 (nearest) on the way into
+  // shared memory, which halves the error of feeding raw fp32 bits to the tensor core (the MMA
+  // truncates): measured normwise 2.4e-4 vs 5.6e-4 at C=256.  SA_B200_TMA_TF32=0 restores raw fp32.
+  static const bool tf32_type = !(getenv("SA_B200_TMA_TF32") && atoi(getenv("SA_B200_TMA_TF32")) == 0);
   const CUtensorMapDataType dt = (tf32_type && swz == CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
                                      ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
@@ -359,7 +363,9 @@ extern "C" int sa_corr_tf32(const float* fmap_l, const float* fmap_r, float* vol
     int rc = make_map(&mo, vol, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "vol");
     if (rc) return rc;
   }
-  const size_t smem = 1024 + (size_t)a.nstage * stage_bytes + (2 * kMaxStages + 2) * sizeof(uint64_t);
+  size_t pipe_bytes = (size_t)a.nstage * stage_bytes;
+  if (pipe_bytes < (size_t)2 * kBM * 128) pipe_bytes = (size_t)2 * kBM * 128;
+  const size_t smem = 1024 + pipe_bytes + (2 * kMaxStages + 2) * sizeof(uint64_t);
   static thread_local size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(corr_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -92,13 +92,13 @@ __global__ void __launch_bounds__(THREADS) lookup_vec_kernel(const LookupArgs a)
       const int t = item % TILE;
       const int i = item / TILE;
       const float nx = __shfl_down_sync(0xffffffffu, q[n].x, 1);
-      const float f = fr[n], g = 1.0f - fr[n];
+      const float f = fr[n];
       float* so = s_out + ((v * NL + i) * NT) * SP + t;
       const int k0 = kb[n];
-      if ((unsigned)(k0 + 0) < (unsigned)NT) so[(k0 + 0) * SP] = g * q[n].x + f * q[n].y;
-      if ((unsigned)(k0 + 1) < (unsigned)NT) so[(k0 + 1) * SP] = g * q[n].y + f * q[n].z;
-      if ((unsigned)(k0 + 2) < (unsigned)NT) so[(k0 + 2) * SP] = g * q[n].z + f * q[n].w;
-      if ((unsigned)(k0 + 3) < (unsigned)NT) so[(k0 + 3) * SP] = g * q[n].w + f * nx;
+      if ((unsigned)(k0 + 0) < (unsigned)NT) so[(k0 + 0) * SP] = blend(q[n].x, q[n].y, f);
+      if ((unsigned)(k0 + 1) < (unsigned)NT) so[(k0 + 1) * SP] = blend(q[n].y, q[n].z, f);
+      if ((unsigned)(k0 + 2) < (unsigned)NT) so[(k0 + 2) * SP] = blend(q[n].z, q[n].w, f);
+      if ((unsigned)(k0 + 3) < (unsigned)NT) so[(k0 + 3) * SP] = blend(q[n].w, nx, f);
     }
   }
   __syncthreads();
@@ -159,7 +159,7 @@ __global__ void lookup_generic_kernel(const LookupArgs a) {
       for (int k = 0; k < nt; ++k) {
         const int c1 = start + k + 1;
         const float nxt = (c1 >= 0 && c1 < wi) ? rowp[c1] : 0.f;
-        outp[(long long)(i * nt + k) * H * wout] = (1.0f - f) * prev + f * nxt;
+        outp[(long long)(i * nt + k) * H * wout] = blend(prev, nxt, f);
         prev = nxt;
       }
     }

@@ -1,0 +1,349 @@
+// Line-packed pyramid + lookup (A3 + A4 for num_levels = 4, radius = 4, W3 % 8 == 0 - the model's
+// configuration; reference: models/stereoanywhere/corr.py:76-115).
+//
+// Why: on B200 every L2 miss fetches a whole 128-byte line from HBM (measured: random 16..128-byte
+// reads all cost 128 B of dram__bytes_read).  A lookup needs four 10-float windows per pixel, one per
+// level, each in a different row of a different array: >= 4 lines (~590 B measured) for 160 useful
+// bytes.  The packed layout stores, for every pixel row and every block q of 8 level-0 columns, ONE
+// line that is sufficient for any x with floor(x) in [8q, 8q+8):
+//     slots  0..16  L0[8q-4 .. 8q+12]
+//     slots 17..21  L1[4q-4], L1[4q-3], L1[4q+6], L1[4q+7], L1[4q+8]
+//     slots 22..26  L2[2q-4], L2[2q-3], L2[2q+4], L2[2q+5], L2[2q+6]
+//     slots 27..31  L3[ q-4], L3[ q-3], L3[ q+3], L3[ q+4], L3[ q+5]
+// The remaining window entries are re-derived in registers with the pyramid's own formula
+// 0.5*(a+b) - L1[4q-2..4q+5] from the stored L0, L2[2q-2..2q+3] from L1, L3[q-2..q+2] from L2 - so the
+// result is bit-identical to pooling first and looking up afterwards.  Entries outside [0, W_i)
+// are stored as zeros (grid_sample's zero padding), blocks q = -5 .. W/8+3 cover every x for which
+// any tap of any level is inside the image.  One lookup = one line per (pixel, volume): 128 B read
+// + 144 B written, below the 308 B/px "algorithmic" figure of the unpacked formulation.
+#include "sa_common.cuh"
+
+namespace sa {
+
+constexpr int kQMin = -5;                       // first block index
+__host__ __device__ inline int packed_blocks(int W) { return W / 8 + 9; }  // q in [-5, W/8 + 3]
+
+// slot -> (level, offset): the entry stored in slot s of block q is L_level[(q << (3 - level)) + off]
+__host__ __device__ inline void slot_map(int s, int& level, int& off) {
+  if (s < 17) {
+    level = 0;
+    off = s - 4;
+    return;
+  }
+  const int t = s - 17;
+  level = 1 + t / 5;
+  const int r = t % 5;
+  const int hi = level == 1 ? 6 : (level == 2 ? 4 : 3);
+  off = r < 2 ? r - 4 : hi + (r - 2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pack: one warp per volume row.  The (optionally truncation-masked) row and its three pooled levels
+// are formed in shared memory, then gathered into nblk lines with coalesced 128-bit stores.
+// ---------------------------------------------------------------------------------------------
+struct PackArgs {
+  const float* src;
+  float* packed;
+  long long rows;
+  int W;
+  const float* disp;  // truncation (optional)
+  const float* conf;
+  float gain, one_minus_gain;
+  int w2_size;
+};
+
+template <bool TRUNC>
+__global__ void __launch_bounds__(256) pack_kernel(const PackArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int W = a.W;
+  const int per_warp = (W + W / 2 + W / 4 + W / 8 + 3) & ~3;  // keep every warp's slab 16-byte aligned
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s0 = sm + warp * per_warp;
+  float* s1 = s0 + W;
+  float* s2 = s1 + W / 2;
+  float* s3 = s2 + W / 4;
+  const int nblk = packed_blocks(W);
+  // a lane always writes the same 4 slots (v & 7 == lane & 7): resolve them once
+  int lv[4], off[4], lbase[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    slot_map((lane & 7) * 4 + e, lv[e], off[e]);
+    lbase[e] = lv[e] == 0 ? 0 : (lv[e] == 1 ? W : (lv[e] == 2 ? W + W / 2 : W + W / 2 + W / 4));
+  }
+  const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp; row < a.rows; row += warps_total) {
+    const float* src = a.src + row * W;
+    float c = 0.f, centre = 0.f, omc = 1.f;
+    if (TRUNC) {
+      c = __ldg(a.conf + row);
+      omc = 1.0f - c;
+      centre = (float)(int)(row % a.w2_size) - __ldg(a.disp + row);
+    }
+    for (int v = lane; v < W / 4; v += 32) {
+      float4 q = ld_stream_v4(src + 4 * v);
+      if (TRUNC) {
+        const float w3 = (float)(4 * v);
+        q.x *= trunc_mask(centre, w3, c, omc, a.gain, a.one_minus_gain);
+        q.y *= trunc_mask(centre, w3 + 1.0f, c, omc, a.gain, a.one_minus_gain);
+        q.z *= trunc_mask(centre, w3 + 2.0f, c, omc, a.gain, a.one_minus_gain);
+        q.w *= trunc_mask(centre, w3 + 3.0f, c, omc, a.gain, a.one_minus_gain);
+      }
+      *reinterpret_cast<float4*>(s0 + 4 * v) = q;
+      *reinterpret_cast<float2*>(s1 + 2 * v) = make_float2((q.x + q.y) * 0.5f, (q.z + q.w) * 0.5f);
+    }
+    __syncwarp();
+    for (int j = lane; j < W / 4; j += 32) s2[j] = (s1[2 * j] + s1[2 * j + 1]) * 0.5f;
+    __syncwarp();
+    for (int j = lane; j < W / 8; j += 32) s3[j] = (s2[2 * j] + s2[2 * j + 1]) * 0.5f;
+    __syncwarp();
+    float* dst = a.packed + row * (long long)nblk * 32;
+    for (int v = lane; v < nblk * 8; v += 32) {  // one float4 = 4 slots of one block
+      const int q = (v >> 3) + kQMin;
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int idx = q * (8 >> lv[e]) + off[e];
+        o[e] = (idx >= 0 && idx < (W >> lv[e])) ? s0[lbase[e] + idx] : 0.0f;
+      }
+      st_stream_v4(dst + 4 * v, make_float4(o[0], o[1], o[2], o[3]));
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lookup from the packed layout
+// ---------------------------------------------------------------------------------------------
+struct PLookupArgs {
+  const float* packed[2];
+  float* out[2];
+  const float* coords;
+  long long coords_bstride;
+  int HW, W3, nblk;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+
+template <int N>
+__device__ __forceinline__ void shift_if(float (&v)[N], bool on, int by, int keep) {
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if (i < keep && i + by < N) v[i] = on ? v[i + by] : v[i];
+}
+
+template <int NV, int TILE>
+__global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupArgs a) {
+  constexpr int THREADS = NV * TILE;
+  constexpr int NC = 36;
+  constexpr int SP = TILE + 4;
+  constexpr int STAGE_FLOATS = NV * TILE * 32;
+  constexpr int OUT_FLOATS = NV * NC * SP;
+  constexpr int BUF_FLOATS = STAGE_FLOATS > OUT_FLOATS ? STAGE_FLOATS : OUT_FLOATS;
+  extern __shared__ __align__(16) float smem[];
+  float* buf = smem;                                        // staging lines, later the output tile
+  float* s_x = smem + BUF_FLOATS;                           // [TILE] x coordinate
+  int* s_blk = reinterpret_cast<int*>(s_x + TILE);          // [TILE] block index or -1
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int hw0 = blockIdx.x * TILE;
+  const int npx = min(TILE, a.HW - hw0);
+  const long long row0 = (long long)b * a.HW + hw0;
+
+  if (tid < TILE) {
+    float x = 0.f;
+    int blk = -1;
+    if (tid < npx) {
+      x = __ldg(a.coords + (long long)b * a.coords_bstride + hw0 + tid);
+      const float fl = fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
+      const int q = ((int)fl >> 3) - kQMin;
+      if (q >= 0 && q < a.nblk) blk = q;
+    }
+    s_x[tid] = x;
+    s_blk[tid] = blk;
+  }
+  __syncthreads();
+
+  // ---- stage one line per (pixel, volume): 8 lanes x 16 B, chunk c of pixel p lands at chunk c ^ (p & 7)
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int idx = tid + n * THREADS;
+    const int unit = idx >> 3, ch = idx & 7;
+    const int v = unit / TILE, p = unit % TILE;
+    float* dst = buf + unit * 32 + ((ch ^ (p & 7)) << 2);
+    const int blk = s_blk[p];
+    if (blk >= 0)
+      cp_async16(dst, (v ? a.packed[1] : a.packed[0]) + ((row0 + p) * a.nblk + blk) * 32 + ch * 4);
+    else
+      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- thread (pixel p, volume v): its line -> registers
+  const int p = tid % TILE, v = tid / TILE;
+  float l0[17 + 3], e[12];  // l0: slots 0..19 (17 L0 values + 3 spill-over), e: slots 20..31
+  {
+    const float* src = buf + tid * 32;  // unit index == tid
+#pragma unroll
+    for (int ch = 0; ch < 5; ++ch) {
+      const float4 t = *reinterpret_cast<const float4*>(src + ((ch ^ (p & 7)) << 2));
+      l0[4 * ch] = t.x; l0[4 * ch + 1] = t.y; l0[4 * ch + 2] = t.z; l0[4 * ch + 3] = t.w;
+    }
+#pragma unroll
+    for (int ch = 5; ch < 8; ++ch) {
+      const float4 t = *reinterpret_cast<const float4*>(src + ((ch ^ (p & 7)) << 2));
+      e[4 * (ch - 5)] = t.x; e[4 * (ch - 5) + 1] = t.y; e[4 * (ch - 5) + 2] = t.z; e[4 * (ch - 5) + 3] = t.w;
+    }
+  }
+  __syncthreads();  // staging is dead: `buf` becomes the [channel][pixel] output tile
+
+  // full windows of levels 1..3 (relative index 0 = first stored entry of the level)
+  float l1[13], l2[11], l3[10];
+  l1[0] = l0[17]; l1[1] = l0[18]; l1[10] = l0[19]; l1[11] = e[0]; l1[12] = e[1];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) l1[2 + t] = (l0[2 * t] + l0[2 * t + 1]) * 0.5f;
+  l2[0] = e[2]; l2[1] = e[3]; l2[8] = e[4]; l2[9] = e[5]; l2[10] = e[6];
+#pragma unroll
+  for (int t = 0; t < 6; ++t) l2[2 + t] = (l1[2 * t] + l1[2 * t + 1]) * 0.5f;
+  l3[0] = e[7]; l3[1] = e[8]; l3[7] = e[9]; l3[8] = e[10]; l3[9] = e[11];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) l3[2 + t] = (l2[2 * t] + l2[2 * t + 1]) * 0.5f;
+
+  const float x = s_x[p];
+  const float flx = fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
+  const int x0 = (int)flx;
+  // window starts inside the stored ranges: a0 in [0,8), a1 in [0,4), a2 in [0,2), a3 = 0
+  {
+    float w[17];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) w[i] = l0[i];
+    shift_if(w, (x0 & 1) != 0, 1, 16);
+    shift_if(w, (x0 & 2) != 0, 2, 14);
+    shift_if(w, (x0 & 4) != 0, 4, 10);
+    const float f = x - floorf(x);
+    float* so = buf + (v * NC + 0) * SP + p;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) so[k * SP] = blend(w[k], w[k + 1], f);
+  }
+  {
+    const int x1 = x0 >> 1;
+    shift_if(l1, (x1 & 1) != 0, 1, 12);
+    shift_if(l1, (x1 & 2) != 0, 2, 10);
+    const float xs = x * 0.5f;
+    const float f = xs - floorf(xs);
+    float* so = buf + (v * NC + 9) * SP + p;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) so[k * SP] = blend(l1[k], l1[k + 1], f);
+  }
+  {
+    const int x2 = x0 >> 2;
+    shift_if(l2, (x2 & 1) != 0, 1, 10);
+    const float xs = x * 0.25f;
+    const float f = xs - floorf(xs);
+    float* so = buf + (v * NC + 18) * SP + p;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) so[k * SP] = blend(l2[k], l2[k + 1], f);
+  }
+  {
+    const float xs = x * 0.125f;
+    const float f = xs - floorf(xs);
+    float* so = buf + (v * NC + 27) * SP + p;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) so[k * SP] = blend(l3[k], l3[k + 1], f);
+  }
+  __syncthreads();
+
+  // ---- [channel][pixel] tile -> NCHW
+  if ((a.HW & 3) == 0) {
+    constexpr int T4 = TILE / 4;
+    for (int idx = tid; idx < NV * NC * T4; idx += THREADS) {
+      const int c = idx / T4;
+      const int t = (idx % T4) * 4;
+      if (t < npx) {
+        const float4 val = *reinterpret_cast<const float4*>(buf + c * SP + t);
+        const int vv = c / NC, cc = c - vv * NC;
+        st_stream_v4((vv ? a.out[1] : a.out[0]) + ((long long)b * NC + cc) * a.HW + hw0 + t, val);
+      }
+    }
+  } else {
+    for (int idx = tid; idx < NV * NC * TILE; idx += THREADS) {
+      const int c = idx / TILE, t = idx % TILE;
+      if (t < npx) {
+        const int vv = c / NC, cc = c - vv * NC;
+        (vv ? a.out[1] : a.out[0])[((long long)b * NC + cc) * a.HW + hw0 + t] = buf[c * SP + t];
+      }
+    }
+  }
+}
+
+template <int NV>
+static int launch_packed(const PLookupArgs& a, int B, cudaStream_t st) {
+  constexpr int TILE = 128;
+  constexpr int NC = 36, SP = TILE + 4;
+  constexpr int buf_floats = (NV * TILE * 32 > NV * NC * SP) ? NV * TILE * 32 : NV * NC * SP;
+  const size_t smem = (size_t)(buf_floats + 2 * TILE) * sizeof(float);
+  auto kern = lookup_packed_kernel<NV, TILE>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) SA_FAIL((int)e, "sa_lookup_packed: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  dim3 grid((a.HW + TILE - 1) / TILE, B);
+  kern<<<grid, NV * TILE, smem, st>>>(a);
+  return finish_launch("sa_lookup_packed");
+}
+
+}  // namespace sa
+
+extern "C" int64_t sa_packed_row_floats(int W) { return (int64_t)sa::packed_blocks(W) * 32; }
+
+extern "C" int sa_pack_pyramid(const float* src, int64_t rows, int W, const float* trunc_disp, const float* trunc_conf,
+                               double trunc_gain, int w2_size, float* packed, void* stream) {
+  using namespace sa;
+  SA_REQUIRE(src && packed && rows > 0, SA_E_INVALID, "sa_pack_pyramid: null pointer / no rows");
+  SA_REQUIRE(W >= 8 && W % 8 == 0, SA_E_UNSUPPORTED, "sa_pack_pyramid: W must be a positive multiple of 8 (got %d)", W);
+  SA_REQUIRE(aligned16(src) && aligned16(packed), SA_E_ALIGN, "sa_pack_pyramid: pointers must be 16-byte aligned");
+  const bool trunc = trunc_disp != nullptr;
+  if (trunc)
+    SA_REQUIRE(trunc_conf && w2_size > 0 && rows % w2_size == 0, SA_E_INVALID,
+               "sa_pack_pyramid: truncation needs conf and rows %% w2_size == 0");
+  PackArgs a = {};
+  a.src = src; a.packed = packed; a.rows = rows; a.W = W;
+  a.disp = trunc_disp; a.conf = trunc_conf;
+  a.gain = (float)trunc_gain; a.one_minus_gain = (float)(1.0 - trunc_gain);
+  a.w2_size = w2_size;
+  const int warps = 8;
+  const size_t smem = (size_t)warps * ((W + W / 2 + W / 4 + W / 8 + 3) & ~3) * sizeof(float);
+  SA_REQUIRE(smem <= 200 * 1024, SA_E_UNSUPPORTED, "sa_pack_pyramid: W = %d too wide", W);
+  auto kern = trunc ? pack_kernel<true> : pack_kernel<false>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) SA_FAIL((int)e, "sa_pack_pyramid: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  const long long want = (rows + warps - 1) / warps;
+  const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
+  kern<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(a);
+  return finish_launch("sa_pack_pyramid");
+}
+
+extern "C" int sa_lookup_packed(const float* packed_a, const float* packed_b, int W3, const float* coords,
+                                int64_t coords_bstride, float* out_a, float* out_b, int B, int H, int W, void* stream) {
+  using namespace sa;
+  SA_REQUIRE(packed_a && coords && out_a, SA_E_INVALID, "sa_lookup_packed: null pointer");
+  SA_REQUIRE((packed_b == nullptr) == (out_b == nullptr), SA_E_INVALID, "sa_lookup_packed: packed_b / out_b must come together");
+  SA_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 31), SA_E_INVALID, "sa_lookup_packed: bad sizes");
+  SA_REQUIRE(W3 >= 8 && W3 % 8 == 0, SA_E_UNSUPPORTED, "sa_lookup_packed: W3 must be a multiple of 8");
+  SA_REQUIRE(aligned16(packed_a) && aligned16(out_a) && (!packed_b || (aligned16(packed_b) && aligned16(out_b))), SA_E_ALIGN,
+             "sa_lookup_packed: pointers must be 16-byte aligned");
+  (void)num_sms();
+  PLookupArgs a = {};
+  a.packed[0] = packed_a; a.packed[1] = packed_b;
+  a.out[0] = out_a; a.out[1] = out_b;
+  a.coords = coords; a.coords_bstride = coords_bstride;
+  a.HW = H * W; a.W3 = W3; a.nblk = packed_blocks(W3);
+  return packed_b ? launch_packed<2>(a, B, (cudaStream_t)stream) : launch_packed<1>(a, B, (cudaStream_t)stream);
+}

@@ -185,6 +185,64 @@ def _lookup2(levels_a: Sequence[torch.Tensor], levels_b: Sequence[torch.Tensor],
     return out_a, out_b
 
 
+def packable(num_levels: int, radius: int, w3: int, pad) -> bool:
+    """The line-packed fast path covers the model's configuration (corr_levels=4, corr_radius=4,
+    quarter-resolution width a multiple of 8, no pad)."""
+    return num_levels == 4 and radius == 4 and w3 >= 8 and w3 % 8 == 0 and list(pad) == [0, 0]
+
+
+def _pack_pyramid(vol: torch.Tensor, trunc_disp: Optional[torch.Tensor], trunc_conf: Optional[torch.Tensor],
+                  trunc_gain: float) -> torch.Tensor:
+    """vol [rows, W3] -> packed [rows, (W3/8 + 9) * 32] (csrc/packed.cu)."""
+    _cuda_f32(vol, "fullcorr")
+    _req(vol.dim() == 2 and vol.is_contiguous(), "pack expects a contiguous [rows, W] view")
+    rows, w = vol.shape
+    _req(w >= 8 and w % 8 == 0, "packed pyramid needs W3 % 8 == 0")
+    lib = _lib.load()
+    packed = torch.empty((rows, int(lib.sa_packed_row_floats(w))), dtype=torch.float32, device=vol.device)
+    with torch.cuda.device(vol.device):
+        if trunc_disp is not None:
+            _cuda_f32(trunc_disp, "trunc_disp")
+            _cuda_f32(trunc_conf, "trunc_conf")
+            trunc_disp, trunc_conf = trunc_disp.contiguous(), trunc_conf.contiguous()
+            _req(trunc_disp.numel() == rows and trunc_conf.numel() == rows,
+                 "truncation maps must be [B,1,H,W2] matching the volume")
+            rc = lib.sa_pack_pyramid(vol.data_ptr(), rows, w, trunc_disp.data_ptr(), trunc_conf.data_ptr(), trunc_gain,
+                                     trunc_disp.shape[-1], packed.data_ptr(), _stream_ptr(vol))
+        else:
+            rc = lib.sa_pack_pyramid(vol.data_ptr(), rows, w, None, None, 0.0, 0, packed.data_ptr(), _stream_ptr(vol))
+    _lib.check(rc, "sa_pack_pyramid")
+    return packed
+
+
+def _lookup_packed(packed_a: torch.Tensor, packed_b: Optional[torch.Tensor], w3: int, coords: torch.Tensor):
+    coords, b, h, w = _coords_view(coords)
+    _cuda_f32(packed_a, "packed pyramid")
+    lib = _lib.load()
+    rowf = int(lib.sa_packed_row_floats(w3))
+    _req(packed_a.shape == (b * h * w, rowf), "coords do not match the volume this block was built from")
+    out_a = torch.empty((b, 36, h, w), dtype=torch.float32, device=coords.device)
+    out_b = None
+    if packed_b is not None:
+        _cuda_f32(packed_b, "packed pyramid")
+        _req(packed_b.shape == packed_a.shape, "lookup of two volumes needs identical geometry")
+        out_b = torch.empty_like(out_a)
+    with torch.cuda.device(coords.device):
+        rc = lib.sa_lookup_packed(packed_a.data_ptr(), packed_b.data_ptr() if packed_b is not None else None, w3,
+                                  coords.data_ptr(), coords.stride(0), out_a.data_ptr(),
+                                  out_b.data_ptr() if out_b is not None else None, b, h, w, _stream_ptr(coords))
+    _lib.check(rc, "sa_lookup_packed")
+    return out_a, out_b
+
+
+def _lookup_packed1(packed: torch.Tensor, w3: int, coords: torch.Tensor) -> torch.Tensor:
+    return _lookup_packed(packed, None, w3, coords)[0]
+
+
+def _lookup_packed2(packed_a: torch.Tensor, packed_b: torch.Tensor, w3: int, coords: torch.Tensor):
+    return _lookup_packed(packed_a, packed_b, w3, coords)
+
+
 def _truncate(vol: Optional[torch.Tensor], disp: torch.Tensor, conf: torch.Tensor, gain: float) -> torch.Tensor:
     _cuda_f32(disp, "disp")
     _cuda_f32(conf, "conf")
@@ -271,6 +329,9 @@ _LIBDEF.define("corr_volume(Tensor fmap_l, Tensor fmap_r, str precision, float p
 _LIBDEF.define("pyramid(Tensor vol_rows, int num_levels, Tensor? trunc_disp, Tensor? trunc_conf, float trunc_gain) -> Tensor[]")
 _LIBDEF.define("lookup(Tensor[] levels, int[] widths, Tensor coords, int radius, int pad0, int pad1) -> Tensor")
 _LIBDEF.define("lookup2(Tensor[] levels_a, Tensor[] levels_b, int[] widths, Tensor coords, int radius) -> (Tensor, Tensor)")
+_LIBDEF.define("pack_pyramid(Tensor vol_rows, Tensor? trunc_disp, Tensor? trunc_conf, float trunc_gain) -> Tensor")
+_LIBDEF.define("lookup_packed(Tensor packed, int w3, Tensor coords) -> Tensor")
+_LIBDEF.define("lookup_packed2(Tensor packed_a, Tensor packed_b, int w3, Tensor coords) -> (Tensor, Tensor)")
 _LIBDEF.define("truncate(Tensor? vol, Tensor disp, Tensor conf, float gain) -> Tensor")
 _LIBDEF.define("masked_volume(Tensor? vol, Tensor? normals_l, Tensor? normals_r, float post_scale, Tensor mde_l, Tensor mde_r, int n_bins) -> Tensor")
 _LIBDEF.define("corrupt(Tensor vol, Tensor bin_mask, int mode, int shift, Tensor? noise, float gauss_k) -> Tensor")
@@ -279,8 +340,12 @@ _LIBDEF.impl("corr_volume", _corr_volume, "CUDA")
 _LIBDEF.impl("pyramid", _pyramid, "CUDA")
 _LIBDEF.impl("lookup", _lookup, "CUDA")
 _LIBDEF.impl("lookup2", _lookup2, "CUDA")
+_LIBDEF.impl("pack_pyramid", _pack_pyramid, "CUDA")
+_LIBDEF.impl("lookup_packed", _lookup_packed1, "CUDA")
+_LIBDEF.impl("lookup_packed2", _lookup_packed2, "CUDA")
 _LIBDEF.impl("truncate", _truncate, "CUDA")
 _LIBDEF.impl("masked_volume", _masked_volume, "CUDA")
 _LIBDEF.impl("corrupt", _corrupt, "CUDA")
 
-OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "truncate", "masked_volume", "corrupt"]
+OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "lookup_packed", "lookup_packed2",
+            "truncate", "masked_volume", "corrupt"]

@@ -222,6 +222,36 @@ def test_block_vs_oracle_seeded(sa, b, h, w):
         assert maxabs(got, want) < 2e-6 * max(w, 16)
 
 
+@pytest.mark.parametrize("b,h,w", [(1, 5, 24), (2, 7, 312), (1, 3, 128), (1, 2, 768)])
+def test_packed_layout_is_bit_identical_to_levels(sa, b, h, w):
+    """The line-packed fast path (csrc/packed.cu) against the plain pyramid + lookup kernels."""
+    gen = torch.Generator().manual_seed(100 + w)
+    vol = torch.randn(b, h, w, 1, w, generator=gen).to(DEV)
+    disp = (torch.rand(b, 1, h, w, generator=gen) * (w / 4)).to(DEV)
+    conf = torch.rand(b, 1, h, w, generator=gen).to(DEV)
+    B = sa.CorrBlockB200
+    for trunc in (None, (disp, conf, 0.9)):
+        old = B.layout
+        try:
+            B.layout = "levels"
+            ref = B(vol, num_levels=4, radius=4, truncate=trunc)
+            B.layout = "packed"
+            blk = B(vol, num_levels=4, radius=4, truncate=trunc)
+        finally:
+            B.layout = old
+        assert blk._packed is not None and ref._packed is None
+        assert torch.equal(blk.fullcorr, ref.fullcorr)
+        for lp, lr in zip(blk.corr_pyramid, ref.corr_pyramid):
+            assert torch.equal(lp, lr)
+        x = torch.arange(w, dtype=torch.float32).view(1, 1, 1, w).expand(b, 1, h, w)
+        for dx in (-torch.rand(b, 1, h, w, generator=gen) * (w / 4), torch.rand(b, 1, h, w, generator=gen) * 60,
+                   (torch.rand(b, 1, h, w, generator=gen) - 0.5) * 4 * w, -torch.randint(0, 9, (b, 1, h, w), generator=gen).float()):
+            coords = torch.cat([x + dx, torch.zeros(b, 1, h, w)], 1).to(DEV)
+            assert torch.equal(blk(coords), ref(coords))
+            pa, pb = B.lookup_pair(blk, blk, coords)
+            assert torch.equal(pa, ref(coords)) and torch.equal(pb, pa)
+
+
 def test_lookup_pair_equals_two_calls(sa):
     gen = torch.Generator().manual_seed(11)
     b, h, w = 2, 12, 312

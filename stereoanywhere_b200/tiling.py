@@ -1,0 +1,177 @@
+"""Tile-sharded full-resolution inference (BASELINE config 4) and batch sharding (config 3).
+
+Host-side plumbing only (torch + torch.distributed).  The geometry reproduces the reference's
+MapReduce wrapper so that a tile-sharded run returns the reference's tiled result:
+
+* tile enumeration  - mapreduce_v2/tile_wrapper.py:101-120 (`TileWrapper._enumerate_tiles`):
+  stride = tile - overlap, border tiles shifted back inside the image; the reference emits the
+  clamped last row / column more than once and accumulates the duplicates (harmless after
+  normalisation, but they do change the blend where tiles overlap).  `unique=False` keeps that
+  behaviour bit for bit; `unique=True` runs every distinct tile ONCE and weights it by its
+  multiplicity - the same stitched image up to fp32 summation order, with 10 instead of 12 model
+  runs for the `middlebury` preset on 1984x2880.  The multi-GPU path shards the distinct tiles.
+* per-tile replicate pad to a multiple of 32 and un-pad - tile_wrapper.py:226-247.
+* blend weight clamp(sin(pi y) sin(pi x), 1e-4) and weighted accumulation - tile_wrapper.py:36-49,
+  328-362; final `stitched / clamp(weight, 1e-4)` - tile_wrapper.py:185.
+
+Multi-GPU: tiles are independent units.  Every rank runs its share of tiles, accumulates
+`disp * w` and `w` locally, and ONE collective - `reduce(sum)` of a `[2,H,W]` fp32 tensor to rank 0 -
+stitches the image.  Batch sharding needs one `all_gather` of the disparities.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tile = Tuple[int, int, int, int]  # y0, y1, x0, x1
+
+#: the reference's presets that matter for the BASELINE configs (mapreduce_v2/tile_presets.py:37-127):
+#: name -> (tile_height, tile_width, overlap)
+PRESETS = {
+    "default": (448, 448, 96),
+    "middlebury": (1120, 672, 112),
+    "kitti": (448, 1344, 128),
+    "sceneflow": (448, 448, 112),
+    "booster": (896, 1120, 224),
+}
+
+
+def _axis_starts(extent: int, tile: int, overlap: int) -> List[Tuple[int, int]]:
+    step = tile - overlap
+    if step <= 0:
+        raise ValueError("overlap must be smaller than the tile")
+    spans = []
+    pos = 0
+    while pos < extent:
+        hi = min(pos + tile, extent)
+        spans.append((max(0, hi - tile), hi))
+        pos += step
+    return spans
+
+
+def enumerate_tiles(height: int, width: int, tile_h: int, tile_w: int, overlap: int, unique: bool = False) -> List[Tile]:
+    """Row-major list of (y0, y1, x0, x1); `unique=True` drops repeated tiles (first occurrence kept)."""
+    tiles = [(y0, y1, x0, x1) for (y0, y1) in _axis_starts(height, tile_h, overlap)
+             for (x0, x1) in _axis_starts(width, tile_w, overlap)]
+    return list(dict.fromkeys(tiles)) if unique else tiles
+
+
+def tile_multiplicity(height: int, width: int, tile_h: int, tile_w: int, overlap: int):
+    """Distinct tiles in first-occurrence order with the number of times the reference emits them."""
+    counts = {}
+    for t in enumerate_tiles(height, width, tile_h, tile_w, overlap):
+        counts[t] = counts.get(t, 0) + 1
+    return list(counts.items())
+
+
+def blend_weight(h: int, w: int, device=None) -> torch.Tensor:
+    """[h, w] cosine window of the reference (tile_wrapper.py:36-49)."""
+    if h <= 0 or w <= 0:
+        raise ValueError("Tile dimensions must be positive")
+    y = torch.linspace(0, 1, h, device=device)
+    x = torch.linspace(0, 1, w, device=device)
+    wy = torch.sin(torch.pi * y).unsqueeze(1)
+    wx = torch.sin(torch.pi * x).unsqueeze(0)
+    return torch.clamp(wy * wx, min=1e-4)
+
+
+def pad_to_32(h: int, w: int) -> List[int]:
+    """[left, right, top, bottom] of the replicate pad (tile_wrapper.py:226-229, test.py:204-207)."""
+    ph = (32 - h % 32) % 32
+    pw = (32 - w % 32) % 32
+    return [pw // 2, pw - pw // 2, ph // 2, ph - ph // 2]
+
+
+def shard(items: Sequence, rank: int, world: int) -> List:
+    """Round-robin share of `items` for `rank` (tiles differ in cost only at the borders)."""
+    return [it for i, it in enumerate(items) if i % world == rank]
+
+
+def run_tile(model: Callable[..., torch.Tensor], tensors: Sequence[Optional[torch.Tensor]], tile: Tile) -> torch.Tensor:
+    """Crop, replicate-pad to /32, run `model`, negate, un-pad (tile_wrapper.py:208-247)."""
+    y0, y1, x0, x1 = tile
+    pad = pad_to_32(y1 - y0, x1 - x0)
+    args = [None if t is None else F.pad(t[:, :, y0:y1, x0:x1], pad, mode="replicate") for t in tensors]
+    out = model(*args)
+    if isinstance(out, (tuple, list)):
+        out = out[0]
+    disp = -out
+    hd, wd = disp.shape[-2:]
+    return disp[..., pad[2]: hd - pad[3], pad[0]: wd - pad[1]]
+
+
+def tiled_inference(
+    model: Callable[..., torch.Tensor],
+    left: torch.Tensor,
+    right: torch.Tensor,
+    mono_left: Optional[torch.Tensor],
+    mono_right: Optional[torch.Tensor],
+    tile_h: int,
+    tile_w: int,
+    overlap: int,
+    *,
+    group=None,
+    unique: Optional[bool] = None,
+    dst: int = 0,
+) -> Optional[torch.Tensor]:
+    """Tiled inference, tiles sharded over the ranks of `group` (single process when torch.distributed
+    is not initialised).  Returns the stitched `[1,1,H,W]` disparity on rank `dst`, None elsewhere.
+
+    `unique=None` picks the reference's duplicate-keeping enumeration for a single process (bit-exact
+    parity with `TileWrapper.forward`) and the de-duplicated one when sharding."""
+    import torch.distributed as dist
+
+    distributed = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if distributed else 0
+    world = dist.get_world_size(group) if distributed else 1
+    b, _, height, width = left.shape
+    if b != 1:
+        raise ValueError("tiled inference supports batch size == 1 (tile_wrapper.py:148-149)")
+    if height <= tile_h and width <= tile_w:  # single-shot path of the reference (tile_wrapper.py:151-153)
+        if rank != dst:
+            return None
+        out = model(left, right, mono_left, mono_right)
+        out = out[0] if isinstance(out, (tuple, list)) else out
+        return -out
+    if unique is None:
+        unique = world > 1
+    if unique:
+        work = tile_multiplicity(height, width, tile_h, tile_w, overlap)
+    else:
+        work = [(t, 1) for t in enumerate_tiles(height, width, tile_h, tile_w, overlap)]
+    acc = torch.zeros(2, height, width, dtype=torch.float32, device=left.device)  # [disp*w, w]
+    for (y0, y1, x0, x1), mult in shard(work, rank, world):
+        disp = run_tile(model, (left, right, mono_left, mono_right), (y0, y1, x0, x1)).to(acc.device)
+        wgt = blend_weight(y1 - y0, x1 - x0, device=acc.device)
+        for _ in range(mult):  # the reference accumulates a repeated tile once per repeat
+            acc[0, y0:y1, x0:x1] += disp[0, 0].float() * wgt
+            acc[1, y0:y1, x0:x1] += wgt
+    if world > 1:
+        dist.reduce(acc, dst=dst, op=dist.ReduceOp.SUM, group=group)  # the path's only collective
+        if rank != dst:
+            return None
+    num, den = acc[0], acc[1]
+    out = torch.where(den > 0, num / torch.clamp(den, min=1e-4), num)
+    return out.view(1, 1, height, width)
+
+
+def shard_batch(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:
+    """Contiguous slice of the batch for `rank` (config 3: 64 pairs -> 8 per GPU)."""
+    b = t.shape[0]
+    per = math.ceil(b / world)
+    return t[rank * per: min(b, (rank + 1) * per)]
+
+
+def gather_batch(local: torch.Tensor, group=None) -> torch.Tensor:
+    """all_gather of per-rank `[B/N, ...]` results back into `[B, ...]` (equal shares)."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return local
+    world = dist.get_world_size(group)
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local.contiguous(), group=group)
+    return torch.cat(parts, dim=0)

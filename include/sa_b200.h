@@ -113,12 +113,16 @@ int sa_lookup2(const float* const* h_levels_a, const float* const* h_levels_b, c
  *   sa_pack_pyramid           src: rows x W3 fp32 -> packed: rows x sa_packed_row_floats(W3);
  *                             optional truncation as in sa_pyramid (the masked level 0 is not
  *                             materialised)
+ *   sa_pack_pyramid_normals   the same for the mono volume of A2 (C = 3 unit normals, divisor, post_scale
+ *                             as in sa_corr_fp32) computed on the fly: the volume itself is never written
  *   sa_lookup_packed          `CorrBlock1D.__call__` for one (packed_b == out_b == NULL) or two
  *                             volumes; coords / out as in sa_lookup, pad = 0.
  */
 int64_t sa_packed_row_floats(int W3);
 int sa_pack_pyramid(const float* src, int64_t rows, int W3, const float* trunc_disp, const float* trunc_conf,
                     double trunc_gain, int w2_size, float* packed, void* stream);
+int sa_pack_pyramid_normals(const float* normals_l, const float* normals_r, float divisor, float post_scale, int B,
+                            int H, int W2, int W3, float* packed, void* stream);
 int sa_lookup_packed(const float* packed_a, const float* packed_b, int W3, const float* coords,
                      int64_t coords_bstride, float* out_a, float* out_b, int B, int H, int W, void* stream);
 

@@ -16,6 +16,8 @@ brackets):
   * `CorrBlockB200(vol, truncate=(disp, conf, gain))`  - builds the pyramid of T*vol in the same
     pass that forms the product  [stereoanywhere.py:203, 253-255];
   * `CorrBlockB200.mono_corr(nL, nR)`                  - A2 with the `1.73 *` folded in  [:136];
+  * `CorrBlockB200.from_normals(nL, nR)`               - A2 + pyramid in one pass, volume never written
+    [:136, :257-259];
   * `CorrBlockB200.lookup_pair(stereo_fn, mono_fn, coords)` - both per-iteration lookups in one
     launch  [:270-271];
   * `masked_volume(...)`, `truncation_mask(...)`, `corrupt_volume(...)` - A6 / A5 / A7.
@@ -74,8 +76,32 @@ class CorrBlockB200:
     #: "packed" (default; used whenever num_levels=4, radius=4, W3 % 8 == 0, pad=[0,0]) or "levels"
     layout = os.environ.get("SA_B200_LAYOUT", "packed")
 
+    @classmethod
+    def from_normals(cls, normals2: torch.Tensor, normals3: torch.Tensor, num_levels: int = 4, radius: int = 4,
+                     gain: float = 1.73) -> "CorrBlockB200":
+        """The mono block of stereoanywhere.py:136 + :257-259 in one pass: the lookup structure of
+        `gain * corr(nL, nR)` is written straight from the normal maps; the volume itself is only formed
+        if `fullcorr` / `corr_pyramid` are read.  Same values as `cls(cls.mono_corr(nL, nR))`."""
+        _no_grad_check(normals2, normals3)
+        b, c, h, w2 = normals2.shape
+        w3 = normals3.shape[3]
+        if not (cls.layout == "packed" and ops.packable(num_levels, radius, w3, [0, 0])):
+            return cls(cls.mono_corr(normals2, normals3, gain), num_levels=num_levels, radius=radius)
+        self = cls.__new__(cls)
+        self.num_levels, self.radius, self.pad = num_levels, radius, [0, 0]
+        self._normals = (normals2.float(), normals3.float(), float(gain))
+        self._src = None
+        self._truncate = None
+        self._shape = (b, h, w2, w3)
+        self._widths = ops.level_widths(w3, num_levels)
+        self._levels = None
+        self._packed = _OPS.pack_pyramid_normals(self._normals[0], self._normals[1], float(gain))
+        return self
+
     def _build_levels(self):
         if self._levels is None:
+            if self._src is None:  # block built by from_normals: form the volume on demand
+                self._src = CorrBlockB200.mono_corr(*self._normals)
             b, h, w2, w3 = self._shape
             rows = self._src.view(b * h * w2, w3)
             t = self._truncate
@@ -88,6 +114,8 @@ class CorrBlockB200:
         """The volume the lookups see, `[B,H,W2,1,W3]` (reference attribute, corr.py:83).  With
         `truncate=` this is the product T*V (formed on first access when the packed layout is in use)."""
         if self._truncate is None:
+            if self._src is None:
+                self._src = CorrBlockB200.mono_corr(*self._normals)
             return self._src
         b, h, w2, w3 = self._shape
         return self._build_levels()[0].view(b, h, w2, 1, w3)

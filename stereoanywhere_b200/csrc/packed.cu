@@ -43,6 +43,11 @@ __host__ __device__ inline void slot_map(int s, int& level, int& off) {
 // ---------------------------------------------------------------------------------------------
 struct PackArgs {
   const float* src;
+  // alternative source: the C=3 normals volume computed on the fly (A2), row = (b*H + h)*W2 + w2
+  const float* nl;
+  const float* nr;
+  int H, W2;
+  float divisor, post_scale;
   float* packed;
   long long rows;
   int W;
@@ -52,7 +57,7 @@ struct PackArgs {
   int w2_size;
 };
 
-template <bool TRUNC>
+template <bool TRUNC, bool NORMALS>
 __global__ void __launch_bounds__(256) pack_kernel(const PackArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int W = a.W;
@@ -79,8 +84,32 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackArgs a) {
       omc = 1.0f - c;
       centre = (float)(int)(row % a.w2_size) - __ldg(a.disp + row);
     }
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+    const float* nrp = nullptr;
+    long long plane3 = 0;
+    if (NORMALS) {  // same FMA order as corr_simt_kernel: bit-identical to sa_corr_fp32 + sa_pack_pyramid
+      const long long bh = row / a.W2;
+      const int w2 = (int)(row - bh * a.W2);
+      const long long b = bh / a.H, h = bh - b * a.H;
+      const long long plane2 = (long long)a.H * a.W2;
+      plane3 = (long long)a.H * W;
+      const float* nlp = a.nl + (b * 3 * a.H + h) * a.W2 + w2;
+      n0 = __ldg(nlp); n1 = __ldg(nlp + plane2); n2 = __ldg(nlp + 2 * plane2);
+      nrp = a.nr + (b * 3 * a.H + h) * (long long)W;
+    }
     for (int v = lane; v < W / 4; v += 32) {
-      float4 q = ld_stream_v4(src + 4 * v);
+      float4 q;
+      if (NORMALS) {
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(nrp + 4 * v));
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(nrp + plane3 + 4 * v));
+        const float4 r2 = __ldg(reinterpret_cast<const float4*>(nrp + 2 * plane3 + 4 * v));
+        q.x = __fdiv_rn(fmaf(n2, r2.x, fmaf(n1, r1.x, fmaf(n0, r0.x, 0.f))), a.divisor) * a.post_scale;
+        q.y = __fdiv_rn(fmaf(n2, r2.y, fmaf(n1, r1.y, fmaf(n0, r0.y, 0.f))), a.divisor) * a.post_scale;
+        q.z = __fdiv_rn(fmaf(n2, r2.z, fmaf(n1, r1.z, fmaf(n0, r0.z, 0.f))), a.divisor) * a.post_scale;
+        q.w = __fdiv_rn(fmaf(n2, r2.w, fmaf(n1, r1.w, fmaf(n0, r0.w, 0.f))), a.divisor) * a.post_scale;
+      } else {
+        q = ld_stream_v4(src + 4 * v);
+      }
       if (TRUNC) {
         const float w3 = (float)(4 * v);
         q.x *= trunc_mask(centre, w3, c, omc, a.gain, a.one_minus_gain);
@@ -301,6 +330,25 @@ static int launch_packed(const PLookupArgs& a, int B, cudaStream_t st) {
 
 extern "C" int64_t sa_packed_row_floats(int W) { return (int64_t)sa::packed_blocks(W) * 32; }
 
+namespace sa {
+static int launch_pack(PackArgs& a, bool trunc, bool normals, cudaStream_t st) {
+  const int W = a.W;
+  const int warps = 8;
+  const size_t smem = (size_t)warps * ((W + W / 2 + W / 4 + W / 8 + 3) & ~3) * sizeof(float);
+  SA_REQUIRE(smem <= 200 * 1024, SA_E_UNSUPPORTED, "sa_pack_pyramid: W = %d too wide", W);
+  void (*kern)(const PackArgs) = normals ? pack_kernel<false, true>
+                                         : (trunc ? pack_kernel<true, false> : pack_kernel<false, false>);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) SA_FAIL((int)e, "sa_pack_pyramid: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  }
+  const long long want = (a.rows + warps - 1) / warps;
+  const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
+  kern<<<grid, warps * 32, smem, st>>>(a);
+  return finish_launch("sa_pack_pyramid");
+}
+}  // namespace sa
+
 extern "C" int sa_pack_pyramid(const float* src, int64_t rows, int W, const float* trunc_disp, const float* trunc_conf,
                                double trunc_gain, int w2_size, float* packed, void* stream) {
   using namespace sa;
@@ -316,18 +364,21 @@ extern "C" int sa_pack_pyramid(const float* src, int64_t rows, int W, const floa
   a.disp = trunc_disp; a.conf = trunc_conf;
   a.gain = (float)trunc_gain; a.one_minus_gain = (float)(1.0 - trunc_gain);
   a.w2_size = w2_size;
-  const int warps = 8;
-  const size_t smem = (size_t)warps * ((W + W / 2 + W / 4 + W / 8 + 3) & ~3) * sizeof(float);
-  SA_REQUIRE(smem <= 200 * 1024, SA_E_UNSUPPORTED, "sa_pack_pyramid: W = %d too wide", W);
-  auto kern = trunc ? pack_kernel<true> : pack_kernel<false>;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) SA_FAIL((int)e, "sa_pack_pyramid: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  }
-  const long long want = (rows + warps - 1) / warps;
-  const int grid = (int)(want < (long long)num_sms() * 8 ? want : (long long)num_sms() * 8);
-  kern<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(a);
-  return finish_launch("sa_pack_pyramid");
+  return launch_pack(a, trunc, false, (cudaStream_t)stream);
+}
+
+extern "C" int sa_pack_pyramid_normals(const float* normals_l, const float* normals_r, float divisor, float post_scale,
+                                       int B, int H, int W2, int W3, float* packed, void* stream) {
+  using namespace sa;
+  SA_REQUIRE(normals_l && normals_r && packed, SA_E_INVALID, "sa_pack_pyramid_normals: null pointer");
+  SA_REQUIRE(B > 0 && H > 0 && W2 > 0 && divisor != 0.f, SA_E_INVALID, "sa_pack_pyramid_normals: bad sizes");
+  SA_REQUIRE(W3 >= 8 && W3 % 8 == 0, SA_E_UNSUPPORTED, "sa_pack_pyramid_normals: W3 must be a positive multiple of 8");
+  SA_REQUIRE(aligned16(normals_r) && aligned16(packed), SA_E_ALIGN, "sa_pack_pyramid_normals: pointers must be 16-byte aligned");
+  PackArgs a = {};
+  a.nl = normals_l; a.nr = normals_r; a.H = H; a.W2 = W2;
+  a.divisor = divisor; a.post_scale = post_scale;
+  a.packed = packed; a.rows = (long long)B * H * W2; a.W = W3;
+  return launch_pack(a, false, true, (cudaStream_t)stream);
 }
 
 extern "C" int sa_lookup_packed(const float* packed_a, const float* packed_b, int W3, const float* coords,

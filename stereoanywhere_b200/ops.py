@@ -23,6 +23,24 @@ def _stream_ptr(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NOGUARD = _NoGuard()
+
+
+def _on(dev: torch.device):
+    """Device guard that costs nothing in the common single-device-per-process case."""
+    if dev.index is None or torch.cuda.current_device() == dev.index:
+        return _NOGUARD
+    return torch.cuda.device(dev)
+
+
 def _req(cond: bool, msg: str):
     if not cond:
         raise ValueError(msg)
@@ -63,7 +81,7 @@ def _corr_volume(fmap_l: torch.Tensor, fmap_r: torch.Tensor, precision: str, pos
     # the reference divides by torch.sqrt(torch.tensor(C)): a float32 scalar (corr.py:132)
     divisor = float(torch.sqrt(torch.tensor(c)))
     lib = _lib.load()
-    with torch.cuda.device(fmap_l.device):
+    with _on(fmap_l.device):
         if precision == "fp32":
             rc = lib.sa_corr_fp32(fmap_l.data_ptr(), fmap_r.data_ptr(), vol.data_ptr(), b, c, h, w2, w3, divisor,
                                   post_scale, _stream_ptr(vol))
@@ -99,7 +117,7 @@ def _pyramid(vol: torch.Tensor, num_levels: int, trunc_disp: Optional[torch.Tens
              "truncation maps must be [B,1,H,W2] matching the volume")
         w2_size = trunc_disp.shape[-1]
         levels = [torch.empty_like(vol)]
-    with torch.cuda.device(dev):
+    with _on(dev):
         st = _stream_ptr(vol)
         if num_levels == 1:
             if trunc:
@@ -161,7 +179,7 @@ def _lookup(levels: Sequence[torch.Tensor], widths: Sequence[int], coords: torch
     _req(0 <= pad0 and 0 <= pad1 and pad0 + pad1 < w, "bad pad")
     out = torch.empty((b, n * (2 * radius + 1), h, w - pad0 - pad1), dtype=torch.float32, device=coords.device)
     lib = _lib.load()
-    with torch.cuda.device(coords.device):
+    with _on(coords.device):
         rc = lib.sa_lookup(ptrs, wid, pit, n, radius, coords.data_ptr(), coords.stride(0), out.data_ptr(), b, h, w,
                            pad0, pad1, _stream_ptr(coords))
     _lib.check(rc, "sa_lookup")
@@ -178,7 +196,7 @@ def _lookup2(levels_a: Sequence[torch.Tensor], levels_b: Sequence[torch.Tensor],
     out_a = torch.empty((b, n * (2 * radius + 1), h, w), dtype=torch.float32, device=coords.device)
     out_b = torch.empty_like(out_a)
     lib = _lib.load()
-    with torch.cuda.device(coords.device):
+    with _on(coords.device):
         rc = lib.sa_lookup2(ptrs_a, ptrs_b, wid, pit_a, pit_b, n, radius, coords.data_ptr(), coords.stride(0),
                             out_a.data_ptr(), out_b.data_ptr(), b, h, w, _stream_ptr(coords))
     _lib.check(rc, "sa_lookup2")
@@ -200,7 +218,7 @@ def _pack_pyramid(vol: torch.Tensor, trunc_disp: Optional[torch.Tensor], trunc_c
     _req(w >= 8 and w % 8 == 0, "packed pyramid needs W3 % 8 == 0")
     lib = _lib.load()
     packed = torch.empty((rows, int(lib.sa_packed_row_floats(w))), dtype=torch.float32, device=vol.device)
-    with torch.cuda.device(vol.device):
+    with _on(vol.device):
         if trunc_disp is not None:
             _cuda_f32(trunc_disp, "trunc_disp")
             _cuda_f32(trunc_conf, "trunc_conf")
@@ -212,6 +230,25 @@ def _pack_pyramid(vol: torch.Tensor, trunc_disp: Optional[torch.Tensor], trunc_c
         else:
             rc = lib.sa_pack_pyramid(vol.data_ptr(), rows, w, None, None, 0.0, 0, packed.data_ptr(), _stream_ptr(vol))
     _lib.check(rc, "sa_pack_pyramid")
+    return packed
+
+
+def _pack_pyramid_normals(normals_l: torch.Tensor, normals_r: torch.Tensor, post_scale: float) -> torch.Tensor:
+    """A2 + A3 fused: packed pyramid of post_scale * corr(nL, nR) straight from the normal maps."""
+    _cuda_f32(normals_l, "normals_l")
+    _cuda_f32(normals_r, "normals_r")
+    b, c, h, w2 = normals_l.shape
+    w3 = normals_r.shape[3]
+    _req(c == 3 and normals_r.shape[:3] == (b, 3, h), "normals must be [B,3,H,W]")
+    _req(w3 >= 8 and w3 % 8 == 0, "packed pyramid needs W3 % 8 == 0")
+    normals_l, normals_r = normals_l.contiguous(), normals_r.contiguous()
+    lib = _lib.load()
+    packed = torch.empty((b * h * w2, int(lib.sa_packed_row_floats(w3))), dtype=torch.float32, device=normals_l.device)
+    divisor = float(torch.sqrt(torch.tensor(3)))
+    with _on(normals_l.device):
+        rc = lib.sa_pack_pyramid_normals(normals_l.data_ptr(), normals_r.data_ptr(), divisor, post_scale, b, h, w2, w3,
+                                         packed.data_ptr(), _stream_ptr(packed))
+    _lib.check(rc, "sa_pack_pyramid_normals")
     return packed
 
 
@@ -227,7 +264,7 @@ def _lookup_packed(packed_a: torch.Tensor, packed_b: Optional[torch.Tensor], w3:
         _cuda_f32(packed_b, "packed pyramid")
         _req(packed_b.shape == packed_a.shape, "lookup of two volumes needs identical geometry")
         out_b = torch.empty_like(out_a)
-    with torch.cuda.device(coords.device):
+    with _on(coords.device):
         rc = lib.sa_lookup_packed(packed_a.data_ptr(), packed_b.data_ptr() if packed_b is not None else None, w3,
                                   coords.data_ptr(), coords.stride(0), out_a.data_ptr(),
                                   out_b.data_ptr() if out_b is not None else None, b, h, w, _stream_ptr(coords))
@@ -258,7 +295,7 @@ def _truncate(vol: Optional[torch.Tensor], disp: torch.Tensor, conf: torch.Tenso
         w3 = w2
         out = torch.empty((b, 1, h, w2, w3), dtype=torch.float32, device=disp.device)
     lib = _lib.load()
-    with torch.cuda.device(disp.device):
+    with _on(disp.device):
         rc = lib.sa_truncate(vol.data_ptr() if vol is not None else None, disp.data_ptr(), conf.data_ptr(), gain,
                              out.data_ptr(), b * h * w2, w2, w3, _stream_ptr(disp))
     _lib.check(rc, "sa_truncate")
@@ -279,7 +316,7 @@ def _masked_volume(vol: Optional[torch.Tensor], normals_l: Optional[torch.Tensor
     mde_l, mde_r = mde_l.contiguous(), mde_r.contiguous()
     out = torch.empty((b, n_bins, h, w2, w3), dtype=torch.float32, device=mde_l.device)
     lib = _lib.load()
-    with torch.cuda.device(mde_l.device):
+    with _on(mde_l.device):
         if vol is not None:
             _cuda_f32(vol, "vol")
             vol = vol.contiguous()
@@ -312,7 +349,7 @@ def _corrupt(vol: torch.Tensor, bin_mask: torch.Tensor, mode: int, shift: int, n
         _req(noise.numel() == b * h * w2, "noise must be [B,1,H,W2,1]")
     out = torch.empty_like(vol)
     lib = _lib.load()
-    with torch.cuda.device(vol.device):
+    with _on(vol.device):
         rc = lib.sa_corrupt(vol.data_ptr(), bin_mask.data_ptr(), mode, shift,
                             noise.data_ptr() if noise is not None else None, gauss_k, out.data_ptr(), b, h, w2, w3,
                             _stream_ptr(vol))
@@ -330,6 +367,7 @@ _LIBDEF.define("pyramid(Tensor vol_rows, int num_levels, Tensor? trunc_disp, Ten
 _LIBDEF.define("lookup(Tensor[] levels, int[] widths, Tensor coords, int radius, int pad0, int pad1) -> Tensor")
 _LIBDEF.define("lookup2(Tensor[] levels_a, Tensor[] levels_b, int[] widths, Tensor coords, int radius) -> (Tensor, Tensor)")
 _LIBDEF.define("pack_pyramid(Tensor vol_rows, Tensor? trunc_disp, Tensor? trunc_conf, float trunc_gain) -> Tensor")
+_LIBDEF.define("pack_pyramid_normals(Tensor normals_l, Tensor normals_r, float post_scale) -> Tensor")
 _LIBDEF.define("lookup_packed(Tensor packed, int w3, Tensor coords) -> Tensor")
 _LIBDEF.define("lookup_packed2(Tensor packed_a, Tensor packed_b, int w3, Tensor coords) -> (Tensor, Tensor)")
 _LIBDEF.define("truncate(Tensor? vol, Tensor disp, Tensor conf, float gain) -> Tensor")
@@ -341,11 +379,12 @@ _LIBDEF.impl("pyramid", _pyramid, "CUDA")
 _LIBDEF.impl("lookup", _lookup, "CUDA")
 _LIBDEF.impl("lookup2", _lookup2, "CUDA")
 _LIBDEF.impl("pack_pyramid", _pack_pyramid, "CUDA")
+_LIBDEF.impl("pack_pyramid_normals", _pack_pyramid_normals, "CUDA")
 _LIBDEF.impl("lookup_packed", _lookup_packed1, "CUDA")
 _LIBDEF.impl("lookup_packed2", _lookup_packed2, "CUDA")
 _LIBDEF.impl("truncate", _truncate, "CUDA")
 _LIBDEF.impl("masked_volume", _masked_volume, "CUDA")
 _LIBDEF.impl("corrupt", _corrupt, "CUDA")
 
-OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "lookup_packed", "lookup_packed2",
+OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "lookup_packed", "lookup_packed2",
             "truncate", "masked_volume", "corrupt"]

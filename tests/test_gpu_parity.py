@@ -252,6 +252,25 @@ def test_packed_layout_is_bit_identical_to_levels(sa, b, h, w):
             assert torch.equal(pa, ref(coords)) and torch.equal(pb, pa)
 
 
+def test_from_normals_equals_mono_corr_block(sa, golden_path):
+    """A2 + pyramid fused (`from_normals`) against the two-step path, bit for bit, and the golden volume."""
+    gen = torch.Generator().manual_seed(77)
+    B = sa.CorrBlockB200
+    for (b, h, w) in [(2, 5, 312), (1, 3, 24)]:
+        nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w, generator=gen), dim=1).to(DEV)
+        nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w, generator=gen), dim=1).to(DEV)
+        fused = B.from_normals(nl, nr)
+        two = B(B.mono_corr(nl, nr))
+        assert fused._packed is not None and torch.equal(fused._packed, two._packed)
+        assert torch.equal(fused.fullcorr, two.fullcorr)
+        x = torch.arange(w, dtype=torch.float32).view(1, 1, 1, w).expand(b, 1, h, w)
+        coords = torch.cat([x - torch.rand(b, 1, h, w, generator=gen) * (w / 4), torch.zeros(b, 1, h, w)], 1).to(DEV)
+        assert torch.equal(fused(coords), two(coords))
+    g = golden_path
+    blk = B.from_normals(G(g["a2_nl"]), G(g["a2_nr"]))
+    assert normwise(blk.fullcorr, g["a2_vol"]) < 2e-6
+
+
 def test_lookup_pair_equals_two_calls(sa):
     gen = torch.Generator().manual_seed(11)
     b, h, w = 2, 12, 312

@@ -18,7 +18,7 @@ constexpr int kChunk = 16;
 
 __global__ void __launch_bounds__(256)
 corr_simt_kernel(const float* __restrict__ fl, const float* __restrict__ fr, float* __restrict__ vol, int C, int H,
-                 int W2, int W3, int tiles_m, int tiles_n, float divisor, float post_scale) {
+                 int W2, int W3, int tiles_m, int tiles_n, float divisor, float inv_divisor, float post_scale) {
   __shared__ __align__(16) float sA[kChunk][kTile];
   __shared__ __align__(16) float sB[kChunk][kTile];
 
@@ -78,7 +78,7 @@ corr_simt_kernel(const float* __restrict__ fl, const float* __restrict__ fr, flo
     const int n = n0 + tx * 4;
     float o[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = __fdiv_rn(acc[i][j], divisor) * post_scale;
+    for (int j = 0; j < 4; ++j) o[j] = div_const(acc[i][j], divisor, inv_divisor) * post_scale;
     if (vec && n + 3 < W3) {
       st_stream_v4(orow + n, make_float4(o[0], o[1], o[2], o[3]));
     } else {
@@ -102,6 +102,6 @@ extern "C" int sa_corr_fp32(const float* fmap_l, const float* fmap_r, float* vol
   const long long blocks = (long long)B * H * tiles_m * tiles_n;
   SA_REQUIRE(blocks < (1ll << 31), SA_E_UNSUPPORTED, "sa_corr_fp32: too many tiles");
   corr_simt_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(fmap_l, fmap_r, vol, C, H, W2, W3, tiles_m,
-                                                                      tiles_n, divisor, post_scale);
+                                                                      tiles_n, divisor, (float)(1.0 / (double)divisor), post_scale);
   return finish_launch("sa_corr_fp32");
 }

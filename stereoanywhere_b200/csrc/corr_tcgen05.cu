@@ -108,6 +108,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// One lane of a fully converged warp (the operands around it stay provably warp-uniform, so the
+// compiler keeps them in uniform registers instead of serialising over "active lanes").
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 struct CorrTcArgs {
   int C, H, W2, W3;
   int m_tiles, n_tiles, BN;  // BN: accumulator columns per tile (multiple of 32, <= 256)
@@ -142,7 +150,8 @@ corr_tf32_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constan
   uint64_t* acc_empty = acc_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const int kchunks = a.C / kBK;
 
   if (warp == 0 && lane == 0) {
@@ -171,52 +180,56 @@ corr_tf32_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      uint32_t it = 0;  // slab counter across tiles
-      for (long long tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
-        long long t = tile;
-        const int tn = (int)(t % a.n_tiles); t /= a.n_tiles;
-        const int tm = (int)(t % a.m_tiles);
-        const int bh = (int)(t / a.m_tiles);
-        const int b = bh / a.H, h = bh % a.H;
-        const int m0 = tm * kBM, n0 = tn * a.BN;
-        // boxes wholly outside the image are neither loaded nor counted: their accumulator rows /
-        // columns are clipped by the output tensor map
-        int a_boxes = 0, b_boxes = 0;
-        for (int g = 0; g < kBM / kBox; ++g) a_boxes += (m0 + g * kBox < a.W2);
-        for (int g = 0; g < n_boxes_b; ++g) b_boxes += (n0 + g * kBox < a.W3);
-        for (int kc = 0; kc < kchunks; ++kc, ++it) {
-          const int s = it % a.nstage;
-          const uint32_t ph = (it / a.nstage) & 1u;
-          mbar_wait(&empty[s], ph ^ 1u);
-          mbar_expect_tx(&full[s], (uint32_t)(a_boxes + b_boxes) * kBoxBytes);
+    // ------------------------------------------------------------------ TMA producer (whole warp loops,
+    // one elected lane issues: addresses and coordinates stay in uniform registers)
+    uint32_t it = 0;  // slab counter across tiles
+    for (long long tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
+      long long t = tile;
+      const int tn = (int)(t % a.n_tiles); t /= a.n_tiles;
+      const int tm = (int)(t % a.m_tiles);
+      const int bh = (int)(t / a.m_tiles);
+      const int b = bh / a.H, h = bh % a.H;
+      const int m0 = tm * kBM, n0 = tn * a.BN;
+      // boxes wholly outside the image are neither loaded nor counted: their accumulator rows /
+      // columns are clipped by the output tensor map
+      const int a_boxes = min(kBM / kBox, (a.W2 - m0 + kBox - 1) / kBox);
+      const int b_boxes = min(n_boxes_b, (a.W3 - n0 + kBox - 1) / kBox);
+      const uint32_t tx_bytes = (uint32_t)(a_boxes + b_boxes) * kBoxBytes;
+      for (int kc = 0; kc < kchunks; ++kc, ++it) {
+        const int s = it % a.nstage;
+        const uint32_t ph = (it / a.nstage) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&full[s], tx_bytes);
           uint8_t* sa_ = pipe + (size_t)s * stage_bytes;
           uint8_t* sb_ = sa_ + (kBM / kBox) * kBoxBytes;
-          for (int g = 0; g < a_boxes; ++g)
-            tma_load_4d(sa_ + g * kBoxBytes, &map_l, &full[s], m0 + g * kBox, h, kc * kBK, b);
-          for (int g = 0; g < b_boxes; ++g)
-            tma_load_4d(sb_ + g * kBoxBytes, &map_r, &full[s], n0 + g * kBox, h, kc * kBK, b);
+#pragma unroll
+          for (int g = 0; g < kBM / kBox; ++g)
+            if (g < a_boxes) tma_load_4d(sa_ + g * kBoxBytes, &map_l, &full[s], m0 + g * kBox, h, kc * kBK, b);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (g < b_boxes) tma_load_4d(sb_ + g * kBoxBytes, &map_r, &full[s], n0 + g * kBox, h, kc * kBK, b);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      // instruction descriptor: D=f32, A=B=tf32, both MN-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                             ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-      uint32_t it = 0, lt = 0;
-      for (long long tile = blockIdx.x; tile < a.tiles; tile += gridDim.x, ++lt) {
-        const uint32_t ab = lt & 1u;
-        mbar_wait(&acc_empty[ab], ((lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+    // -------------------------------------------------------------------- MMA issuer (same pattern)
+    // instruction descriptor: D=f32, A=B=tf32, both MN-major, N = BN, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    uint32_t it = 0, lt = 0;
+    for (long long tile = blockIdx.x; tile < a.tiles; tile += gridDim.x, ++lt) {
+      const uint32_t ab = lt & 1u;
+      mbar_wait(&acc_empty[ab], ((lt >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + ab * (uint32_t)kTmemCols;
+      for (int kc = 0; kc < kchunks; ++kc, ++it) {
+        const int s = it % a.nstage;
+        const uint32_t ph = (it / a.nstage) & 1u;
+        mbar_wait(&full[s], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + ab * (uint32_t)kTmemCols;
-        for (int kc = 0; kc < kchunks; ++kc, ++it) {
-          const int s = it % a.nstage;
-          const uint32_t ph = (it / a.nstage) & 1u;
-          mbar_wait(&full[s], ph);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa_ = smem_u32(pipe + (size_t)s * stage_bytes);
           const uint32_t sb_ = sa_ + (kBM / kBox) * kBoxBytes;
 #pragma unroll
@@ -226,8 +239,9 @@ corr_tf32_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constan
             umma_tf32(d_tmem, ad, bd, idesc, (uint32_t)((kc | k) != 0));
           }
           umma_commit(&empty[s]);  // slab reusable once these MMAs have read it
+          if (kc == kchunks - 1) umma_commit(&acc_full[ab]);  // accumulator complete
         }
-        umma_commit(&acc_full[ab]);  // accumulator complete
+        __syncwarp();
       }
     }
   } else {

@@ -47,7 +47,7 @@ struct PackArgs {
   const float* nl;
   const float* nr;
   int H, W2;
-  float divisor, post_scale;
+  float divisor, inv_divisor, post_scale;
   float* packed;
   long long rows;
   int W;
@@ -103,10 +103,10 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackArgs a) {
         const float4 r0 = __ldg(reinterpret_cast<const float4*>(nrp + 4 * v));
         const float4 r1 = __ldg(reinterpret_cast<const float4*>(nrp + plane3 + 4 * v));
         const float4 r2 = __ldg(reinterpret_cast<const float4*>(nrp + 2 * plane3 + 4 * v));
-        q.x = __fdiv_rn(fmaf(n2, r2.x, fmaf(n1, r1.x, fmaf(n0, r0.x, 0.f))), a.divisor) * a.post_scale;
-        q.y = __fdiv_rn(fmaf(n2, r2.y, fmaf(n1, r1.y, fmaf(n0, r0.y, 0.f))), a.divisor) * a.post_scale;
-        q.z = __fdiv_rn(fmaf(n2, r2.z, fmaf(n1, r1.z, fmaf(n0, r0.z, 0.f))), a.divisor) * a.post_scale;
-        q.w = __fdiv_rn(fmaf(n2, r2.w, fmaf(n1, r1.w, fmaf(n0, r0.w, 0.f))), a.divisor) * a.post_scale;
+        q.x = div_const(fmaf(n2, r2.x, fmaf(n1, r1.x, fmaf(n0, r0.x, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
+        q.y = div_const(fmaf(n2, r2.y, fmaf(n1, r1.y, fmaf(n0, r0.y, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
+        q.z = div_const(fmaf(n2, r2.z, fmaf(n1, r1.z, fmaf(n0, r0.z, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
+        q.w = div_const(fmaf(n2, r2.w, fmaf(n1, r1.w, fmaf(n0, r0.w, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
       } else {
         q = ld_stream_v4(src + 4 * v);
       }
@@ -376,7 +376,7 @@ extern "C" int sa_pack_pyramid_normals(const float* normals_l, const float* norm
   SA_REQUIRE(aligned16(normals_r) && aligned16(packed), SA_E_ALIGN, "sa_pack_pyramid_normals: pointers must be 16-byte aligned");
   PackArgs a = {};
   a.nl = normals_l; a.nr = normals_r; a.H = H; a.W2 = W2;
-  a.divisor = divisor; a.post_scale = post_scale;
+  a.divisor = divisor; a.inv_divisor = (float)(1.0 / (double)divisor); a.post_scale = post_scale;
   a.packed = packed; a.rows = (long long)B * H * W2; a.W = W3;
   return launch_pack(a, false, true, (cudaStream_t)stream);
 }

@@ -22,7 +22,7 @@ __device__ __forceinline__ int depth_bin(float x, const BinEdges& ed, int n_bins
 template <bool FROM_NORMALS>
 __global__ void __launch_bounds__(256)
 masked_volume_kernel(const float* __restrict__ vol, const float* __restrict__ nl, const float* __restrict__ nr,
-                     float divisor, float post_scale, const float* __restrict__ mde_l,
+                     float divisor, float inv_divisor, float post_scale, const float* __restrict__ mde_l,
                      const float* __restrict__ mde_r, const BinEdges ed, int n_bins, float* __restrict__ out,
                      int H, int W2, int W3, long long nvec) {
   const int W34 = (W3 + 3) >> 2;
@@ -51,7 +51,7 @@ masked_volume_kernel(const float* __restrict__ vol, const float* __restrict__ nl
           float acc = __ldg(pl) * __ldg(pr);
           acc = fmaf(__ldg(pl + hw2), __ldg(pr + (long long)H * W3), acc);
           acc = fmaf(__ldg(pl + 2 * hw2), __ldg(pr + 2ll * H * W3), acc);
-          x = __fdiv_rn(acc, divisor) * post_scale;
+          x = div_const(acc, divisor, inv_divisor) * post_scale;
         } else {
           x = ld_stream_f32(vol + row * W3 + col + e);
         }
@@ -121,10 +121,11 @@ extern "C" int sa_masked_volume(const float* vol, const float* normals_l, const 
   const int grid = (int)(want < (long long)num_sms() * 16 ? want : (long long)num_sms() * 16);
   cudaStream_t st = (cudaStream_t)stream;
   if (vol)
-    masked_volume_kernel<false><<<grid, 256, 0, st>>>(vol, nullptr, nullptr, 1.f, 1.f, mde_l, mde_r, ed, n_bins, out,
+    masked_volume_kernel<false><<<grid, 256, 0, st>>>(vol, nullptr, nullptr, 1.f, 1.f, 1.f, mde_l, mde_r, ed, n_bins, out,
                                                       H, W2, W3, nvec);
   else
-    masked_volume_kernel<true><<<grid, 256, 0, st>>>(nullptr, normals_l, normals_r, divisor, post_scale, mde_l,
+    masked_volume_kernel<true><<<grid, 256, 0, st>>>(nullptr, normals_l, normals_r, divisor, (float)(1.0 / (double)divisor),
+                                                     post_scale, mde_l,
                                                      mde_r, ed, n_bins, out, H, W2, W3, nvec);
   return finish_launch("sa_masked_volume");
 }

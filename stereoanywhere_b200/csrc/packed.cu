@@ -57,10 +57,13 @@ struct PackArgs {
   int w2_size;
 };
 
+constexpr int kPackMaxV4 = 3;  // float4 per lane and row held in registers while prefetching (W <= 384)
+
 template <bool TRUNC, bool NORMALS>
-__global__ void __launch_bounds__(256) pack_kernel(const PackArgs a) {
+__global__ void __launch_bounds__(256, 3) pack_kernel(const PackArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int W = a.W;
+  const int W4 = W >> 2;
   const int per_warp = (W + W / 2 + W / 4 + W / 8 + 3) & ~3;  // keep every warp's slab 16-byte aligned
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* s0 = sm + warp * per_warp;
@@ -68,16 +71,23 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackArgs a) {
   float* s2 = s1 + W / 2;
   float* s3 = s2 + W / 4;
   const int nblk = packed_blocks(W);
-  // a lane always writes the same 4 slots (v & 7 == lane & 7): resolve them once
+  // second half of every line (slots 16..31): a lane always owns the same 4 slots - resolve them once
   int lv[4], off[4], lbase[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    slot_map((lane & 7) * 4 + e, lv[e], off[e]);
+    slot_map(16 + (lane & 3) * 4 + e, lv[e], off[e]);
     lbase[e] = lv[e] == 0 ? 0 : (lv[e] == 1 ? W : (lv[e] == 2 ? W + W / 2 : W + W / 2 + W / 4));
   }
+  const bool prefetch = !NORMALS && (W4 <= 32 * kPackMaxV4);
   const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp; row < a.rows; row += warps_total) {
-    const float* src = a.src + row * W;
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  float4 nxt[kPackMaxV4];
+  if (prefetch && row < a.rows) {
+#pragma unroll
+    for (int i = 0; i < kPackMaxV4; ++i)
+      if (lane + 32 * i < W4) nxt[i] = ld_stream_v4(a.src + row * W + 4 * (lane + 32 * i));
+  }
+  for (; row < a.rows; row += warps_total) {
     float c = 0.f, centre = 0.f, omc = 1.f;
     if (TRUNC) {
       c = __ldg(a.conf + row);
@@ -97,28 +107,37 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackArgs a) {
       n0 = __ldg(nlp); n1 = __ldg(nlp + plane2); n2 = __ldg(nlp + 2 * plane2);
       nrp = a.nr + (b * 3 * a.H + h) * (long long)W;
     }
-    for (int v = lane; v < W / 4; v += 32) {
-      float4 q;
-      if (NORMALS) {
+    auto put_row = [&](int v, float4 q) {
+      if (TRUNC) {
+        trunc_mask_mul4(q, centre, (float)(4 * v), c, omc, a.gain, a.one_minus_gain);
+      }
+      *reinterpret_cast<float4*>(s0 + 4 * v) = q;
+      *reinterpret_cast<float2*>(s1 + 2 * v) = make_float2((q.x + q.y) * 0.5f, (q.z + q.w) * 0.5f);
+    };
+    if (NORMALS) {
+      for (int v = lane; v < W4; v += 32) {
         const float4 r0 = __ldg(reinterpret_cast<const float4*>(nrp + 4 * v));
         const float4 r1 = __ldg(reinterpret_cast<const float4*>(nrp + plane3 + 4 * v));
         const float4 r2 = __ldg(reinterpret_cast<const float4*>(nrp + 2 * plane3 + 4 * v));
+        float4 q;
         q.x = div_const(fmaf(n2, r2.x, fmaf(n1, r1.x, fmaf(n0, r0.x, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
         q.y = div_const(fmaf(n2, r2.y, fmaf(n1, r1.y, fmaf(n0, r0.y, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
         q.z = div_const(fmaf(n2, r2.z, fmaf(n1, r1.z, fmaf(n0, r0.z, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
         q.w = div_const(fmaf(n2, r2.w, fmaf(n1, r1.w, fmaf(n0, r0.w, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
-      } else {
-        q = ld_stream_v4(src + 4 * v);
+        put_row(v, q);
       }
-      if (TRUNC) {
-        const float w3 = (float)(4 * v);
-        q.x *= trunc_mask(centre, w3, c, omc, a.gain, a.one_minus_gain);
-        q.y *= trunc_mask(centre, w3 + 1.0f, c, omc, a.gain, a.one_minus_gain);
-        q.z *= trunc_mask(centre, w3 + 2.0f, c, omc, a.gain, a.one_minus_gain);
-        q.w *= trunc_mask(centre, w3 + 3.0f, c, omc, a.gain, a.one_minus_gain);
+    } else if (prefetch) {
+#pragma unroll
+      for (int i = 0; i < kPackMaxV4; ++i)
+        if (lane + 32 * i < W4) put_row(lane + 32 * i, nxt[i]);
+      const long long nrow = row + warps_total;  // the next row's loads fly while this row is packed
+      if (nrow < a.rows) {
+#pragma unroll
+        for (int i = 0; i < kPackMaxV4; ++i)
+          if (lane + 32 * i < W4) nxt[i] = ld_stream_v4(a.src + nrow * W + 4 * (lane + 32 * i));
       }
-      *reinterpret_cast<float4*>(s0 + 4 * v) = q;
-      *reinterpret_cast<float2*>(s1 + 2 * v) = make_float2((q.x + q.y) * 0.5f, (q.z + q.w) * 0.5f);
+    } else {
+      for (int v = lane; v < W4; v += 32) put_row(v, ld_stream_v4(a.src + row * W + 4 * v));
     }
     __syncwarp();
     for (int j = lane; j < W / 4; j += 32) s2[j] = (s1[2 * j] + s1[2 * j + 1]) * 0.5f;
@@ -126,15 +145,23 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackArgs a) {
     for (int j = lane; j < W / 8; j += 32) s3[j] = (s2[2 * j] + s2[2 * j + 1]) * 0.5f;
     __syncwarp();
     float* dst = a.packed + row * (long long)nblk * 32;
-    for (int v = lane; v < nblk * 8; v += 32) {  // one float4 = 4 slots of one block
-      const int q = (v >> 3) + kQMin;
+    // first half of every line = L0[8q-4 .. 8q+11]: four aligned float4 copies of the row itself
+    for (int v = lane; v < nblk * 4; v += 32) {
+      const int q = (v >> 2) + kQMin;
+      const int col = 8 * q - 4 + 4 * (v & 3);
+      const float4 o = (col >= 0 && col < W) ? *reinterpret_cast<const float4*>(s0 + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+      st_stream_v4(dst + (v >> 2) * 32 + 4 * (v & 3), o);
+    }
+    // second half: L0[8q+12] and the five border entries of each pooled level
+    for (int v = lane; v < nblk * 4; v += 32) {
+      const int q = (v >> 2) + kQMin;
       float o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int idx = q * (8 >> lv[e]) + off[e];
         o[e] = (idx >= 0 && idx < (W >> lv[e])) ? s0[lbase[e] + idx] : 0.0f;
       }
-      st_stream_v4(dst + 4 * v, make_float4(o[0], o[1], o[2], o[3]));
+      st_stream_v4(dst + (v >> 2) * 32 + 16 + 4 * (v & 3), make_float4(o[0], o[1], o[2], o[3]));
     }
     __syncwarp();
   }

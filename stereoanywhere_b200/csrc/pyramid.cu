@@ -46,11 +46,7 @@ __global__ void __launch_bounds__(256) pyramid_vec_kernel(const PyrArgs a, const
         const float c = __ldg(a.conf + row);
         const float centre = (float)(int)(rowi % (IdxT)a.w2_size) - __ldg(a.disp + row);
         const float omc = 1.0f - c, g = a.gain, omg = a.one_minus_gain;
-        const float w3 = (float)(4 * c4);
-        q.x *= trunc_mask(centre, w3, c, omc, g, omg);
-        q.y *= trunc_mask(centre, w3 + 1.0f, c, omc, g, omg);
-        q.z *= trunc_mask(centre, w3 + 2.0f, c, omc, g, omg);
-        q.w *= trunc_mask(centre, w3 + 3.0f, c, omc, g, omg);
+        trunc_mask_mul4(q, centre, (float)(4 * c4), c, omc, g, omg);
         st_stream_v4(a.masked0 + row * (long long)a.W + 4 * c4, q);
       }
     }

@@ -229,14 +229,16 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
 
+    gather_buf = torch.empty((world * b, 1, h, w), dtype=torch.float32, device=dev) if dist is not None else None
+    disp_buf = torch.empty((b, 1, h, w), dtype=torch.float32, device=dev)
+
     def collective(out):
         # the path's only collective: gather the quarter-res disparity of every rank
         if dist is None:
             return None
-        disp = out[2][:, :1].contiguous()
-        parts = [torch.empty_like(disp) for _ in range(world)]
-        dist.all_gather(parts, disp)
-        return parts
+        disp_buf.copy_(out[2][:, :1])
+        dist.all_gather_into_tensor(gather_buf, disp_buf)
+        return gather_buf
 
     for _ in range(max(args.warmup, 3)):
         collective(path.step())

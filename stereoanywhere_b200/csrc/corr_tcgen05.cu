@@ -405,11 +405,9 @@ extern "C" int sa_corr_tf32(const float* fmap_l, const float* fmap_r, float* vol
     if (rc) return rc;
   }
   const size_t smem = 1024 + kStagingBytes + (size_t)a.nstage * stage_bytes + (2 * kMaxStages + 5) * sizeof(uint64_t);
-  static thread_local size_t configured = 0;
-  if (smem > configured) {
+  {  // per device and cheap: always (re)state the dynamic shared-memory opt-in
     cudaError_t e = cudaFuncSetAttribute(corr_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) SA_FAIL((int)e, "sa_corr_tf32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    configured = smem;
   }
   const long long grid = tiles < (long long)num_sms() ? tiles : (long long)num_sms();
   corr_tf32_kernel<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(ml, mr, mo, a);

@@ -1,0 +1,278 @@
+// SURVEY 8f-1 - lookup fused with the motion encoder's front end
+// (reference: models/stereoanywhere/update.py:74,80-84: `relu(convc1(corr))`, `relu(convc1(corr_mono))`,
+// convc1 = Conv2d(36, 64, 1), the SAME weights for both volumes; lookups: stereoanywhere.py:270-271).
+//
+//   out_v[b, n, h, w] = relu( bias[n] + sum_k weight[n, k] * lookup_v[b, k, h, w] ),  v = stereo, mono
+//
+// The 2 x 36-channel lookup result never goes to HBM: the blended taps are written straight into the
+// canonical UMMA operand layout in shared memory (MN-major, 128B swizzle with 32-byte atoms, pixels
+// = M, channels = K padded to 40) and one elected thread issues 2 x 5 tcgen05.mma (M=128, N=64, K=8,
+// TF32, fp32 accumulate in TMEM).  The epilogue reads the accumulator with tcgen05.ld (lane = pixel),
+// adds the bias, applies ReLU and stores channel-major: for every output channel a warp writes 32
+// consecutive pixels = one 128-byte line.
+// Traffic per pixel: 2 x 128 B read, 2 x 256 B written, versus 288 B written + 288 B re-read +
+// 512 B written by lookup + cuDNN 1x1 convolutions.
+#include "sa_common.cuh"
+#include "tc_common.cuh"
+
+namespace sa {
+
+constexpr int kLcTile = 128;           // pixels per CTA = MMA M
+constexpr int kLcK = 40;               // 36 lookup channels padded to a multiple of the MMA K (8)
+constexpr int kLcN = 64;               // convc1 output channels
+constexpr int kLcGroupBytes = kLcK * 128;          // one 32-pixel group of the A operand: 40 rows x 128 B
+constexpr int kLcABytes = 4 * kLcGroupBytes;       // per volume
+constexpr int kLcBBytes = (kLcN / 8) * (kLcK / 4) * 128;  // weights, K-major core matrices (8 x 16 B)
+
+struct LcArgs {
+  const float* packed[2];
+  float* out[2];
+  const float* coords;
+  const float* weight;  // [64][36]
+  const float* bias;    // [64]
+  long long coords_bstride;
+  int HW, nblk;
+};
+
+__device__ __forceinline__ void lc_cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+template <int N>
+__device__ __forceinline__ void lc_shift_if(float (&v)[N], bool on, int by, int keep) {
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if (i < keep && i + by < N) v[i] = on ? v[i + by] : v[i];
+}
+__device__ __forceinline__ float to_tf32(float x) {  // round to nearest (the MMA alone would truncate)
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// byte offset of element (pixel p, channel k) inside one volume's A operand
+__device__ __forceinline__ uint32_t a_off(int p, int k) {
+  const uint32_t off = (uint32_t)(p >> 5) * kLcGroupBytes + (uint32_t)(k >> 2) * 512 + (uint32_t)(k & 3) * 128 +
+                       (uint32_t)(p & 31) * 4;
+  return off ^ (((off >> 7) & 3) << 5);
+}
+
+__global__ void __launch_bounds__(2 * kLcTile) lookup_conv_kernel(const LcArgs a) {
+  constexpr int TILE = kLcTile, THREADS = 2 * kLcTile;
+  extern __shared__ uint8_t lc_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lc_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = base;                                   // 2 x 20 KB A operands; first 32 KB double as line staging
+  uint8_t* sB = base + 2 * kLcABytes;                   // 10 KB weights
+  float* s_bias = reinterpret_cast<float*>(sB + kLcBBytes);
+  float* s_x = s_bias + kLcN;
+  int* s_blk = reinterpret_cast<int*>(s_x + TILE);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_blk + TILE);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int b = blockIdx.y;
+  const int hw0 = blockIdx.x * TILE;
+  const int npx = min(TILE, a.HW - hw0);
+  const long long row0 = (long long)b * a.HW + hw0;
+
+  if (tid < TILE) {
+    float x = 0.f;
+    int blk = -1;
+    if (tid < npx) {
+      x = __ldg(a.coords + (long long)b * a.coords_bstride + hw0 + tid);
+      const float fl = fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
+      const int q = ((int)fl >> 3) + 5;  // blocks start at q = -5 (csrc/packed.cu)
+      if (q >= 0 && q < a.nblk) blk = q;
+    }
+    s_x[tid] = x;
+    s_blk[tid] = blk;
+  }
+  // weights -> K-major 8x(16 B) core matrices, rounded to tf32; channels 36..39 are zero padding
+  for (int e = tid; e < kLcN * kLcK; e += THREADS) {
+    const int n = e / kLcK, k = e % kLcK;
+    const float wv = (k < 36) ? to_tf32(__ldg(a.weight + n * 36 + k)) : 0.0f;
+    *reinterpret_cast<float*>(sB + ((n >> 3) * (kLcK / 4) + (k >> 2)) * 128 + (n & 7) * 16 + (k & 3) * 4) = wv;
+  }
+  if (tid < kLcN) s_bias[tid] = __ldg(a.bias + tid);
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // ---- stage one packed line per (pixel, volume), chunk c of pixel p at chunk c ^ (p & 7)
+  float* stage = reinterpret_cast<float*>(sA);
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const int idx = tid + n * THREADS;
+    const int unit = idx >> 3, ch = idx & 7;
+    const int v = unit / TILE, p = unit % TILE;
+    float* dst = stage + unit * 32 + ((ch ^ (p & 7)) << 2);
+    const int blk = s_blk[p];
+    if (blk >= 0)
+      lc_cp_async16(dst, (v ? a.packed[1] : a.packed[0]) + ((row0 + p) * a.nblk + blk) * 32 + ch * 4);
+    else
+      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  const int p = tid % TILE, v = tid / TILE;
+  float l0[20], e[12];
+  {
+    const float* src = stage + tid * 32;
+#pragma unroll
+    for (int ch = 0; ch < 5; ++ch) {
+      const float4 t = *reinterpret_cast<const float4*>(src + ((ch ^ (p & 7)) << 2));
+      l0[4 * ch] = t.x; l0[4 * ch + 1] = t.y; l0[4 * ch + 2] = t.z; l0[4 * ch + 3] = t.w;
+    }
+#pragma unroll
+    for (int ch = 5; ch < 8; ++ch) {
+      const float4 t = *reinterpret_cast<const float4*>(src + ((ch ^ (p & 7)) << 2));
+      e[4 * (ch - 5)] = t.x; e[4 * (ch - 5) + 1] = t.y; e[4 * (ch - 5) + 2] = t.z; e[4 * (ch - 5) + 3] = t.w;
+    }
+  }
+  __syncthreads();  // staging is dead: the same bytes now become the A operands
+
+  float l1[13], l2[11], l3[10];
+  l1[0] = l0[17]; l1[1] = l0[18]; l1[10] = l0[19]; l1[11] = e[0]; l1[12] = e[1];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) l1[2 + t] = (l0[2 * t] + l0[2 * t + 1]) * 0.5f;
+  l2[0] = e[2]; l2[1] = e[3]; l2[8] = e[4]; l2[9] = e[5]; l2[10] = e[6];
+#pragma unroll
+  for (int t = 0; t < 6; ++t) l2[2 + t] = (l1[2 * t] + l1[2 * t + 1]) * 0.5f;
+  l3[0] = e[7]; l3[1] = e[8]; l3[7] = e[9]; l3[8] = e[10]; l3[9] = e[11];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) l3[2 + t] = (l2[2 * t] + l2[2 * t + 1]) * 0.5f;
+
+  const float x = s_x[p];
+  const int x0 = (int)fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
+  float w0[17];
+#pragma unroll
+  for (int i = 0; i < 17; ++i) w0[i] = l0[i];
+  lc_shift_if(w0, (x0 & 1) != 0, 1, 16);
+  lc_shift_if(w0, (x0 & 2) != 0, 2, 14);
+  lc_shift_if(w0, (x0 & 4) != 0, 4, 10);
+  const int x1 = x0 >> 1;
+  lc_shift_if(l1, (x1 & 1) != 0, 1, 12);
+  lc_shift_if(l1, (x1 & 2) != 0, 2, 10);
+  lc_shift_if(l2, ((x0 >> 2) & 1) != 0, 1, 10);
+
+  uint8_t* Av = sA + v * kLcABytes;
+  {
+    const float f = x - floorf(x);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) *reinterpret_cast<float*>(Av + a_off(p, k)) = to_tf32(blend(w0[k], w0[k + 1], f));
+  }
+  {
+    const float xs = x * 0.5f, f = xs - floorf(xs);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) *reinterpret_cast<float*>(Av + a_off(p, 9 + k)) = to_tf32(blend(l1[k], l1[k + 1], f));
+  }
+  {
+    const float xs = x * 0.25f, f = xs - floorf(xs);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) *reinterpret_cast<float*>(Av + a_off(p, 18 + k)) = to_tf32(blend(l2[k], l2[k + 1], f));
+  }
+  {
+    const float xs = x * 0.125f, f = xs - floorf(xs);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) *reinterpret_cast<float*>(Av + a_off(p, 27 + k)) = to_tf32(blend(l3[k], l3[k + 1], f));
+  }
+#pragma unroll
+  for (int k = 36; k < kLcK; ++k) *reinterpret_cast<float*>(Av + a_off(p, k)) = 0.0f;
+
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core reads
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // D = f32, A = tf32 MN-major (transpose bit 15), B = tf32 K-major, N = 64, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(kLcN >> 3) << 17) |
+                             ((uint32_t)(TILE >> 4) << 24);
+      const uint32_t sb_ = smem_u32(sB);
+#pragma unroll
+      for (int vv = 0; vv < 2; ++vv) {
+        const uint32_t sa_ = smem_u32(sA + vv * kLcABytes);
+#pragma unroll
+        for (int ks = 0; ks < kLcK / 8; ++ks) {
+          const uint64_t ad = make_desc(sa_ + ks * 1024, kLcGroupBytes, 512, 1);
+          const uint64_t bd = make_desc(sb_ + ks * 256, 128, (kLcK / 4) * 128, 0);
+          umma_tf32(tmem + vv * kLcN, ad, bd, idesc, (uint32_t)(ks != 0));
+        }
+      }
+      umma_commit(bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+
+  // ---- epilogue: warp w reads TMEM lanes 32*(w%4).. (its pixels), columns of its volume (w/4)
+  const int vq = warp >> 2, quarter = warp & 3;
+  const int px = quarter * 32 + lane;
+  float* outp = (vq ? a.out[1] : a.out[0]) + ((long long)b * kLcN) * a.HW + hw0 + px;
+  const bool live = px < npx;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(vq * kLcN + half * 32)));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (live) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const int n = half * 32 + c;
+        st_stream_f32(outp + (long long)n * a.HW, fmaxf(__uint_as_float(r[c]) + s_bias[n], 0.0f));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+}
+
+}  // namespace sa
+
+extern "C" int sa_lookup_packed_conv(const float* packed_a, const float* packed_b, int W3, const float* coords,
+                                     int64_t coords_bstride, const float* weight, const float* bias, float* out_a,
+                                     float* out_b, int B, int H, int W, void* stream) {
+  using namespace sa;
+  SA_REQUIRE(packed_a && packed_b && coords && weight && bias && out_a && out_b, SA_E_INVALID,
+             "sa_lookup_packed_conv: null pointer");
+  SA_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 31), SA_E_INVALID,
+             "sa_lookup_packed_conv: bad sizes");
+  SA_REQUIRE(W3 >= 8 && W3 % 8 == 0, SA_E_UNSUPPORTED, "sa_lookup_packed_conv: W3 must be a multiple of 8");
+  SA_REQUIRE(aligned16(packed_a) && aligned16(packed_b), SA_E_ALIGN, "sa_lookup_packed_conv: packed arrays must be 16-byte aligned");
+  LcArgs a = {};
+  a.packed[0] = packed_a; a.packed[1] = packed_b;
+  a.out[0] = out_a; a.out[1] = out_b;
+  a.coords = coords; a.coords_bstride = coords_bstride;
+  a.weight = weight; a.bias = bias;
+  a.HW = H * W;
+  a.nblk = W3 / 8 + 9;
+  const size_t smem = 1024 + 2 * kLcABytes + kLcBBytes + (kLcN + 2 * kLcTile) * sizeof(float) + 32;
+  cudaError_t e = cudaFuncSetAttribute(lookup_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) SA_FAIL((int)e, "sa_lookup_packed_conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  dim3 grid((a.HW + kLcTile - 1) / kLcTile, B);
+  lookup_conv_kernel<<<grid, 2 * kLcTile, smem, (cudaStream_t)stream>>>(a);
+  return finish_launch("sa_lookup_packed_conv");
+}

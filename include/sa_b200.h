@@ -126,6 +126,17 @@ int sa_pack_pyramid_normals(const float* normals_l, const float* normals_r, floa
 int sa_lookup_packed(const float* packed_a, const float* packed_b, int W3, const float* coords,
                      int64_t coords_bstride, float* out_a, float* out_b, int B, int H, int W, void* stream);
 
+/* ---------------------------------------------------------------- lookup + motion-encoder front end
+ * out_v[b,n,h,w] = relu(bias[n] + sum_k weight[n,k] * lookup_v[b,k,h,w]) for the stereo and the mono volume
+ * with the SAME 1x1 convolution (models/stereoanywhere/update.py:74,80-84: `relu(convc1(corr))`,
+ * `relu(convc1(corr_mono))`, convc1 = Conv2d(36, 64, 1)); lookups as in sa_lookup_packed
+ * (stereoanywhere.py:270-271).  weight is [64][36] (the conv weight with its 1x1 dims dropped), bias [64];
+ * out_a / out_b are [B,64,H,W].  The 36-channel lookups are never written to memory: the taps feed a TF32
+ * tcgen05 MMA out of shared memory.  Normwise error vs the fp32 convolution <= 1e-3. */
+int sa_lookup_packed_conv(const float* packed_a, const float* packed_b, int W3, const float* coords,
+                          int64_t coords_bstride, const float* weight, const float* bias, float* out_a, float* out_b,
+                          int B, int H, int W, void* stream);
+
 /* ---------------------------------------------------------------- A5: truncation mask (standalone)
  * mask[b,h,w2,w3] = (1-c) + c * (sigmoid((w2 - d) - w3) * (1-g) + g); writes `out` = mask * vol
  * when vol != NULL, else the mask itself.  Replaces `truncate_corr_volume_v2`

@@ -20,6 +20,7 @@ from . import ops  # noqa: E402  (registers torch.ops.sa_b200.*)
 from .corr import (  # noqa: E402
     CorrBlockB200,
     corrupt_volume,
+    lookup_pair_convc1,
     masked_mono_volume,
     masked_volume,
     truncation_mask,
@@ -31,6 +32,7 @@ __all__ = [
     "masked_volume",
     "masked_mono_volume",
     "corrupt_volume",
+    "lookup_pair_convc1",
     "ops",
 ]
 __version__ = "0.1.0"

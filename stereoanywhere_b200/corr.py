@@ -180,6 +180,22 @@ class CorrBlockB200:
         return (oa, ob) if dt == torch.float32 else (oa.to(dt), ob.to(dt))
 
 
+def lookup_pair_convc1(block_a: CorrBlockB200, block_b: CorrBlockB200, coords: torch.Tensor, weight: torch.Tensor,
+                       bias: torch.Tensor):
+    """`(relu(convc1(block_a(coords))), relu(convc1(block_b(coords))))` in one kernel - the front end of
+    `BasicMotionEncoder.forward` (update.py:80-84; convc1 = Conv2d(36, 64, 1), shared by both volumes) fused
+    into the lookups of stereoanywhere.py:270-271.  TF32 tensor-core product, fp32 accumulate.
+    Falls back to two lookups + torch convolutions when the blocks are not in the packed layout."""
+    _no_grad_check(coords, weight, bias)
+    if (block_a._packed is None or block_b._packed is None or block_a._shape != block_b._shape
+            or weight.shape[0] != 64 or weight.shape[1] != 36):
+        sa_, sb_ = CorrBlockB200.lookup_pair(block_a, block_b, coords)
+        conv = torch.nn.functional.conv2d
+        return torch.relu(conv(sa_, weight, bias)), torch.relu(conv(sb_, weight, bias))
+    return _OPS.lookup_packed_conv(block_a._packed, block_b._packed, block_a._shape[3], coords.float(),
+                                   weight.float(), bias.float())
+
+
 def truncation_mask(disp: torch.Tensor, conf: torch.Tensor, attenuation_gain: float,
                     vol: Optional[torch.Tensor] = None) -> torch.Tensor:
     """`truncate_corr_volume_v2(disp, conf, conf_th=None, attenuation_gain)` (utils/utils.py:216-238);

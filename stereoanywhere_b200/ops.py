@@ -272,6 +272,28 @@ def _lookup_packed(packed_a: torch.Tensor, packed_b: Optional[torch.Tensor], w3:
     return out_a, out_b
 
 
+def _lookup_packed_conv(packed_a: torch.Tensor, packed_b: torch.Tensor, w3: int, coords: torch.Tensor,
+                        weight: torch.Tensor, bias: torch.Tensor):
+    """relu(convc1(lookup_a)), relu(convc1(lookup_b)) without materialising the lookups (csrc/lookup_conv.cu)."""
+    coords, b, h, w = _coords_view(coords)
+    for t, n in ((packed_a, "packed_a"), (packed_b, "packed_b"), (weight, "weight"), (bias, "bias")):
+        _cuda_f32(t, n)
+    lib = _lib.load()
+    rowf = int(lib.sa_packed_row_floats(w3))
+    _req(packed_a.shape == (b * h * w, rowf) and packed_b.shape == packed_a.shape, "coords do not match the volumes")
+    _req(weight.numel() == 64 * 36 and bias.numel() == 64, "convc1 must be Conv2d(36, 64, 1): weight [64,36,1,1], bias [64]")
+    weight = weight.reshape(64, 36).contiguous()
+    bias = bias.contiguous()
+    out_a = torch.empty((b, 64, h, w), dtype=torch.float32, device=coords.device)
+    out_b = torch.empty_like(out_a)
+    with _on(coords.device):
+        rc = lib.sa_lookup_packed_conv(packed_a.data_ptr(), packed_b.data_ptr(), w3, coords.data_ptr(), coords.stride(0),
+                                       weight.data_ptr(), bias.data_ptr(), out_a.data_ptr(), out_b.data_ptr(), b, h, w,
+                                       _stream_ptr(coords))
+    _lib.check(rc, "sa_lookup_packed_conv")
+    return out_a, out_b
+
+
 def _lookup_packed1(packed: torch.Tensor, w3: int, coords: torch.Tensor) -> torch.Tensor:
     return _lookup_packed(packed, None, w3, coords)[0]
 
@@ -370,6 +392,7 @@ _LIBDEF.define("pack_pyramid(Tensor vol_rows, Tensor? trunc_disp, Tensor? trunc_
 _LIBDEF.define("pack_pyramid_normals(Tensor normals_l, Tensor normals_r, float post_scale) -> Tensor")
 _LIBDEF.define("lookup_packed(Tensor packed, int w3, Tensor coords) -> Tensor")
 _LIBDEF.define("lookup_packed2(Tensor packed_a, Tensor packed_b, int w3, Tensor coords) -> (Tensor, Tensor)")
+_LIBDEF.define("lookup_packed_conv(Tensor packed_a, Tensor packed_b, int w3, Tensor coords, Tensor weight, Tensor bias) -> (Tensor, Tensor)")
 _LIBDEF.define("truncate(Tensor? vol, Tensor disp, Tensor conf, float gain) -> Tensor")
 _LIBDEF.define("masked_volume(Tensor? vol, Tensor? normals_l, Tensor? normals_r, float post_scale, Tensor mde_l, Tensor mde_r, int n_bins) -> Tensor")
 _LIBDEF.define("corrupt(Tensor vol, Tensor bin_mask, int mode, int shift, Tensor? noise, float gauss_k) -> Tensor")
@@ -382,9 +405,10 @@ _LIBDEF.impl("pack_pyramid", _pack_pyramid, "CUDA")
 _LIBDEF.impl("pack_pyramid_normals", _pack_pyramid_normals, "CUDA")
 _LIBDEF.impl("lookup_packed", _lookup_packed1, "CUDA")
 _LIBDEF.impl("lookup_packed2", _lookup_packed2, "CUDA")
+_LIBDEF.impl("lookup_packed_conv", _lookup_packed_conv, "CUDA")
 _LIBDEF.impl("truncate", _truncate, "CUDA")
 _LIBDEF.impl("masked_volume", _masked_volume, "CUDA")
 _LIBDEF.impl("corrupt", _corrupt, "CUDA")
 
-OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "lookup_packed", "lookup_packed2",
+OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "lookup_packed", "lookup_packed2", "lookup_packed_conv",
             "truncate", "masked_volume", "corrupt"]

@@ -361,3 +361,25 @@ def test_full_size_properties(sa, cfg):
     xin = torch.rand(b, 1, h, w, device=DEV, generator=gen) * (w - 80) + 40
     oc = ones(torch.cat([xin, torch.zeros_like(xin)], 1))
     assert float((oc[:, :9] - 1.0).abs().max()) < 1e-6
+
+
+def test_lookup_fused_with_convc1(sa):
+    """relu(convc1(lookup)) for both volumes in one kernel vs lookup + fp32 torch conv."""
+    torch.backends.cudnn.allow_tf32 = False
+    gen = torch.Generator().manual_seed(21)
+    B = sa.CorrBlockB200
+    for (b, h, w) in [(1, 4, 128), (2, 9, 312), (1, 3, 40)]:
+        va = torch.randn(b, h, w, 1, w, generator=gen).to(DEV)
+        vb = torch.randn(b, h, w, 1, w, generator=gen).to(DEV)
+        weight = (torch.randn(64, 36, 1, 1, generator=gen) / 6).to(DEV)
+        bias = (torch.randn(64, generator=gen) * 0.1).to(DEV)
+        x = torch.arange(w, dtype=torch.float32).view(1, 1, 1, w).expand(b, 1, h, w)
+        coords = torch.cat([x - torch.rand(b, 1, h, w, generator=gen) * (w / 4), torch.zeros(b, 1, h, w)], 1).to(DEV)
+        ba, bb = B(va), B(vb)
+        fa, fb = sa.lookup_pair_convc1(ba, bb, coords, weight, bias)
+        la, lb = B.lookup_pair(ba, bb, coords)
+        ra = torch.relu(torch.nn.functional.conv2d(la.double(), weight.double(), bias.double()))
+        rb = torch.relu(torch.nn.functional.conv2d(lb.double(), weight.double(), bias.double()))
+        assert fa.shape == (b, 64, h, w) and fa.dtype == torch.float32
+        assert normwise(fa, ra) < 1e-3 and normwise(fb, rb) < 1e-3, (normwise(fa, ra), normwise(fb, rb))
+        assert float(fa.min()) >= 0.0  # ReLU

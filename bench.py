@@ -157,10 +157,10 @@ class GpuPath:
         sa, d = self.sa, self.d
         B = sa.CorrBlockB200
         if self.variant == "fused":
-            vs = B.corr(d["fl"], d["fr"])
-            fs = B(vs, radius=RADIUS, num_levels=LEVELS, truncate=(d["tdisp"], d["tconf"], 0.9))
+            # stereo: corr + truncation + pyramid in the GEMM epilogue (one kernel); mono: normals -> packed
+            fs = B.from_features(d["fl"], d["fr"], radius=RADIUS, num_levels=LEVELS, truncate=(d["tdisp"], d["tconf"], 0.9))
             fm = B.from_normals(d["nl"], d["nr"], radius=RADIUS, num_levels=LEVELS)
-            self.launches += 3
+            self.launches += 2
         else:  # strict reference protocol, op for op (stereoanywhere.py:135-136, 203, 253-259)
             vs = B.corr(d["fl"], d["fr"]).squeeze(3).unsqueeze(1)
             vm = 1.73 * B.corr(d["nl"], d["nr"]).squeeze(3).unsqueeze(1)
@@ -244,7 +244,7 @@ def run_gpu(args):
         collective(path.step())
     g_build = g_look = None
     if args.graph:
-        # The step is ~36 launches of 10-400 us: replay it from two CUDA graphs (volumes + packing, then
+        # The step is ~35 launches of 10-400 us: replay it from two CUDA graphs (volumes + packing, then
         # the 32 lookups) so that the events around the second graph time the lookup kernels alone.
         torch.cuda.synchronize()
         seq = path.coords_seq()
@@ -274,7 +274,7 @@ def run_gpu(args):
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    launches = path.launches if g_build is None else args.steps * (35 if args.variant == "fused" else 69)
+    launches = path.launches if g_build is None else args.steps * (34 if args.variant == "fused" else 69)
     lk_ms = sum(a.elapsed_time(bb) for a, bb in lk_events) / args.steps
     n_lk_launch = ITERS if args.variant == "fused" else 2 * ITERS
     lk_launch_ms = lk_ms / n_lk_launch
@@ -412,8 +412,7 @@ def run_tiled(args):
     torch.cuda.synchronize()
 
     def tile_path(d):
-        vs = B.corr(d["fl"], d["fr"])
-        fs = B(vs, radius=RADIUS, num_levels=LEVELS, truncate=(d["tdisp"], d["tconf"], 0.9))
+        fs = B.from_features(d["fl"], d["fr"], radius=RADIUS, num_levels=LEVELS, truncate=(d["tdisp"], d["tconf"], 0.9))
         fm = B.from_normals(d["nl"], d["nr"], radius=RADIUS, num_levels=LEVELS)
         coords = d["coords0"]
         for _ in range(ITERS):

@@ -126,6 +126,17 @@ int sa_pack_pyramid_normals(const float* normals_l, const float* normals_r, floa
 int sa_lookup_packed(const float* packed_a, const float* packed_b, int W3, const float* coords,
                      int64_t coords_bstride, float* out_a, float* out_b, int B, int H, int W, void* stream);
 
+/* ---------------------------------------------------------------- A1 + A5 + A3 fused (tensor cores -> packed pyramid)
+ * packed = sa_pack_pyramid(T * sa_corr_tf32(L, R)) in ONE kernel: the truncation product and the avg-pooled
+ * pyramid are formed in the GEMM epilogue (TMEM -> registers -> packed lines -> TMA store); the fp32 volume
+ * is never written.  Replaces corr.py:117-132 + utils/utils.py:216-238 / stereoanywhere.py:253-255 +
+ * corr.py:76-91 for the stereo block.  Bit-identical to the two-step path.  trunc_disp / trunc_conf may both
+ * be NULL (no truncation).  Needs C % 32 == 0, W2 % 4 == 0, W3 % 8 == 0, 16-byte aligned pointers;
+ * packed is rows = B*H*W2 by sa_packed_row_floats(W3) floats. */
+int sa_corr_pack_tf32(const float* fmap_l, const float* fmap_r, int B, int C, int H, int W2, int W3, float divisor,
+                      float post_scale, const float* trunc_disp, const float* trunc_conf, double trunc_gain,
+                      float* packed, void* stream);
+
 /* ---------------------------------------------------------------- lookup + motion-encoder front end
  * out_v[b,n,h,w] = relu(bias[n] + sum_k weight[n,k] * lookup_v[b,k,h,w]) for the stereo and the mono volume
  * with the SAME 1x1 convolution (models/stereoanywhere/update.py:74,80-84: `relu(convc1(corr))`,

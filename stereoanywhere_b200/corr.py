@@ -18,6 +18,8 @@ brackets):
   * `CorrBlockB200.mono_corr(nL, nR)`                  - A2 with the `1.73 *` folded in  [:136];
   * `CorrBlockB200.from_normals(nL, nR)`               - A2 + pyramid in one pass, volume never written
     [:136, :257-259];
+  * `CorrBlockB200.from_features(fL, fR, truncate=...)` - A1 + A5 + pyramid in one tensor-core kernel, volume never
+    written  [:135, :203, :253-255];
   * `CorrBlockB200.lookup_pair(stereo_fn, mono_fn, coords)` - both per-iteration lookups in one
     launch  [:270-271];
   * `masked_volume(...)`, `truncation_mask(...)`, `corrupt_volume(...)` - A6 / A5 / A7.
@@ -98,12 +100,47 @@ class CorrBlockB200:
         self._packed = _OPS.pack_pyramid_normals(self._normals[0], self._normals[1], float(gain))
         return self
 
+    @classmethod
+    def from_features(cls, fmap2: torch.Tensor, fmap3: torch.Tensor, num_levels: int = 4, radius: int = 4, *,
+                      truncate: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None) -> "CorrBlockB200":
+        """The stereo block of stereoanywhere.py:135 + :203 + :253-255 in ONE kernel: correlation on the tensor
+        cores, truncation product and pyramid in the GEMM epilogue, written once as the packed pyramid
+        (csrc/corr_pack_tcgen05.cu).  Same values, bit for bit, as
+        `cls(cls.corr(fmap2, fmap3), truncate=truncate)` in tf32 precision; the volume is only formed if
+        `fullcorr` / `corr_pyramid` are read.  Falls back to that two-step form for shapes the fused kernel
+        does not cover, or when `precision == "fp32"`."""
+        _no_grad_check(fmap2, fmap3)
+        b, c, h, w2 = fmap2.shape
+        w3 = fmap3.shape[3]
+        if not (cls.layout == "packed" and cls.precision == "tf32" and ops.packable(num_levels, radius, w3, [0, 0])
+                and ops.corr_packable(c, w2, w3)):
+            return cls(cls.corr(fmap2, fmap3), num_levels=num_levels, radius=radius, truncate=truncate)
+        self = cls.__new__(cls)
+        self.num_levels, self.radius, self.pad = num_levels, radius, [0, 0]
+        self._features = (fmap2.float(), fmap3.float())
+        self._src = None
+        self._truncate = None if truncate is None else (truncate[0], truncate[1], float(truncate[2]))
+        self._shape = (b, h, w2, w3)
+        self._widths = ops.level_widths(w3, num_levels)
+        self._levels = None
+        t = self._truncate
+        self._packed = _OPS.corr_pack(self._features[0], self._features[1], t[0] if t else None, t[1] if t else None,
+                                      t[2] if t else 0.0)
+        return self
+
+    def _source(self) -> torch.Tensor:
+        """The un-truncated volume; formed on demand for blocks built by from_normals / from_features."""
+        if self._src is None:
+            if getattr(self, "_features", None) is not None:
+                self._src = CorrBlockB200.corr(*self._features)
+            else:
+                self._src = CorrBlockB200.mono_corr(*self._normals)
+        return self._src
+
     def _build_levels(self):
         if self._levels is None:
-            if self._src is None:  # block built by from_normals: form the volume on demand
-                self._src = CorrBlockB200.mono_corr(*self._normals)
             b, h, w2, w3 = self._shape
-            rows = self._src.view(b * h * w2, w3)
+            rows = self._source().view(b * h * w2, w3)
             t = self._truncate
             self._levels = list(_OPS.pyramid(rows, self.num_levels, t[0] if t else None, t[1] if t else None,
                                              t[2] if t else 0.0))
@@ -114,9 +151,7 @@ class CorrBlockB200:
         """The volume the lookups see, `[B,H,W2,1,W3]` (reference attribute, corr.py:83).  With
         `truncate=` this is the product T*V (formed on first access when the packed layout is in use)."""
         if self._truncate is None:
-            if self._src is None:
-                self._src = CorrBlockB200.mono_corr(*self._normals)
-            return self._src
+            return self._source()
         b, h, w2, w3 = self._shape
         return self._build_levels()[0].view(b, h, w2, 1, w3)
 

@@ -1,6 +1,7 @@
 // PTX helpers shared by the tensor-core kernels (tcgen05 / TMEM / TMA / mbarrier), sm_100a.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "sa_common.cuh"
 
@@ -92,5 +93,42 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred != 0;
 }
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+inline int make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                    const cuuint32_t* box, CUtensorMapSwizzle swz, const char* what) {
+  EncodeTiledFn fn = encode_fn();
+  SA_REQUIRE(fn != nullptr, SA_E_UNSUPPORTED, "cuTensorMapEncodeTiled unavailable (no driver?)");
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  // Operands are declared TFLOAT32 to the TMA unit: it rounds fp32 -> tf32 (nearest) on the way into
+  // shared memory, which halves the error of feeding raw fp32 bits to the tensor core (the MMA
+  // truncates): measured normwise 2.4e-4 vs 5.6e-4 at C=256.  SA_B200_TMA_TF32=0 restores raw fp32.
+  static const bool tf32_type = !(getenv("SA_B200_TMA_TF32") && atoi(getenv("SA_B200_TMA_TF32")) == 0);
+  const CUtensorMapDataType dt = (tf32_type && swz == CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+                                     ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box,
+                  ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SA_REQUIRE(r == CUDA_SUCCESS, SA_E_INVALID, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what,
+             (int)r);
+  return 0;
+}
+
 
 }  // namespace sa

@@ -252,6 +252,41 @@ def _pack_pyramid_normals(normals_l: torch.Tensor, normals_r: torch.Tensor, post
     return packed
 
 
+def _corr_pack(fmap_l: torch.Tensor, fmap_r: torch.Tensor, trunc_disp: Optional[torch.Tensor],
+               trunc_conf: Optional[torch.Tensor], trunc_gain: float) -> torch.Tensor:
+    """A1 (+A5) + A3 fused: packed pyramid of [T *] corr(L, R) straight from the feature maps
+    (csrc/corr_pack_tcgen05.cu); the volume is never written."""
+    _cuda_f32(fmap_l, "fmap_l")
+    _cuda_f32(fmap_r, "fmap_r")
+    _req(fmap_l.dim() == 4 and fmap_r.dim() == 4, "feature maps must be [B,C,H,W]")
+    b, c, h, w2 = fmap_l.shape
+    _req(fmap_r.shape[:3] == (b, c, h), "left/right feature maps must share B, C, H")
+    w3 = fmap_r.shape[3]
+    _req(corr_packable(c, w2, w3), "corr_pack needs C % 32 == 0, W2 % 4 == 0, W3 % 8 == 0")
+    fmap_l, fmap_r = fmap_l.contiguous(), fmap_r.contiguous()
+    lib = _lib.load()
+    rows = b * h * w2
+    packed = torch.empty((rows, int(lib.sa_packed_row_floats(w3))), dtype=torch.float32, device=fmap_l.device)
+    divisor = float(torch.sqrt(torch.tensor(c)))
+    td = tc = None
+    if trunc_disp is not None:
+        _cuda_f32(trunc_disp, "trunc_disp")
+        _cuda_f32(trunc_conf, "trunc_conf")
+        trunc_disp, trunc_conf = trunc_disp.contiguous(), trunc_conf.contiguous()
+        _req(trunc_disp.numel() == rows and trunc_conf.numel() == rows,
+             "truncation maps must be [B,1,H,W2] matching the left feature map")
+        td, tc = trunc_disp.data_ptr(), trunc_conf.data_ptr()
+    with _on(fmap_l.device):
+        rc = lib.sa_corr_pack_tf32(fmap_l.data_ptr(), fmap_r.data_ptr(), b, c, h, w2, w3, divisor, 1.0, td, tc,
+                                   float(trunc_gain), packed.data_ptr(), _stream_ptr(packed))
+    _lib.check(rc, "sa_corr_pack_tf32")
+    return packed
+
+
+def corr_packable(c: int, w2: int, w3: int) -> bool:
+    return c % 32 == 0 and c >= 32 and w2 % 4 == 0 and w3 >= 8 and w3 % 8 == 0
+
+
 def _lookup_packed(packed_a: torch.Tensor, packed_b: Optional[torch.Tensor], w3: int, coords: torch.Tensor):
     coords, b, h, w = _coords_view(coords)
     _cuda_f32(packed_a, "packed pyramid")
@@ -390,6 +425,7 @@ _LIBDEF.define("lookup(Tensor[] levels, int[] widths, Tensor coords, int radius,
 _LIBDEF.define("lookup2(Tensor[] levels_a, Tensor[] levels_b, int[] widths, Tensor coords, int radius) -> (Tensor, Tensor)")
 _LIBDEF.define("pack_pyramid(Tensor vol_rows, Tensor? trunc_disp, Tensor? trunc_conf, float trunc_gain) -> Tensor")
 _LIBDEF.define("pack_pyramid_normals(Tensor normals_l, Tensor normals_r, float post_scale) -> Tensor")
+_LIBDEF.define("corr_pack(Tensor fmap_l, Tensor fmap_r, Tensor? trunc_disp, Tensor? trunc_conf, float trunc_gain) -> Tensor")
 _LIBDEF.define("lookup_packed(Tensor packed, int w3, Tensor coords) -> Tensor")
 _LIBDEF.define("lookup_packed2(Tensor packed_a, Tensor packed_b, int w3, Tensor coords) -> (Tensor, Tensor)")
 _LIBDEF.define("lookup_packed_conv(Tensor packed_a, Tensor packed_b, int w3, Tensor coords, Tensor weight, Tensor bias) -> (Tensor, Tensor)")
@@ -403,6 +439,7 @@ _LIBDEF.impl("lookup", _lookup, "CUDA")
 _LIBDEF.impl("lookup2", _lookup2, "CUDA")
 _LIBDEF.impl("pack_pyramid", _pack_pyramid, "CUDA")
 _LIBDEF.impl("pack_pyramid_normals", _pack_pyramid_normals, "CUDA")
+_LIBDEF.impl("corr_pack", _corr_pack, "CUDA")
 _LIBDEF.impl("lookup_packed", _lookup_packed1, "CUDA")
 _LIBDEF.impl("lookup_packed2", _lookup_packed2, "CUDA")
 _LIBDEF.impl("lookup_packed_conv", _lookup_packed_conv, "CUDA")
@@ -410,5 +447,5 @@ _LIBDEF.impl("truncate", _truncate, "CUDA")
 _LIBDEF.impl("masked_volume", _masked_volume, "CUDA")
 _LIBDEF.impl("corrupt", _corrupt, "CUDA")
 
-OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "lookup_packed", "lookup_packed2", "lookup_packed_conv",
+OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "corr_pack", "lookup_packed", "lookup_packed2", "lookup_packed_conv",
             "truncate", "masked_volume", "corrupt"]

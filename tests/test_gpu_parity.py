@@ -6,6 +6,8 @@ fp32 SIMT kernel; lookup / pyramid / masks compare fp32 arithmetic and must agre
 absolute on O(1) data (grid_sample's normalise/un-normalise round trip alone is ~1e-5, SURVEY
 Appendix A); pyramid levels are bit-exact (halving is exact).
 """
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -383,3 +385,38 @@ def test_lookup_fused_with_convc1(sa):
         assert fa.shape == (b, 64, h, w) and fa.dtype == torch.float32
         assert normwise(fa, ra) < 1e-3 and normwise(fb, rb) < 1e-3, (normwise(fa, ra), normwise(fb, rb))
         assert float(fa.min()) >= 0.0  # ReLU
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 3, 128, 128), (2, 256, 5, 312, 312), (1, 32, 2, 40, 40), (1, 128, 2, 168, 168),
+                                   (1, 64, 1, 240, 240), (1, 64, 1, 520, 776), (1, 32, 2, 8, 8), (1, 64, 2, 132, 264)])
+@pytest.mark.parametrize("trunc", [False, True])
+def test_corr_pack_fused_matches_two_step(sa, shape, trunc):
+    """A1 (+A5) + A3 in the GEMM epilogue (sa_corr_pack_tf32) vs sa_corr_tf32 -> sa_pack_pyramid: same packed
+    array bit for bit, hence identical lookups; and vs the fp64 closed form within the TF32 tolerance."""
+    b, c, h, w2, w3 = shape
+    gen = torch.Generator().manual_seed(31 + w3)
+    fl = torch.randn(b, c, h, w2, generator=gen).to(DEV)
+    fr = torch.randn(b, c, h, w3, generator=gen).to(DEV)
+    t = None
+    if trunc:
+        t = ((torch.rand(b, 1, h, w2, generator=gen) * (w3 / 4)).to(DEV), torch.rand(b, 1, h, w2, generator=gen).to(DEV), 0.9)
+    B = sa.CorrBlockB200
+    B.precision = "tf32"
+    two = B(B.corr(fl, fr), truncate=t)
+    one = B.from_features(fl, fr, truncate=t)
+    assert one._packed is not None and two._packed is not None
+    assert one._packed.shape == two._packed.shape
+    assert torch.equal(one._packed, two._packed), float((one._packed - two._packed).abs().max())
+    x = torch.arange(w2, dtype=torch.float32).view(1, 1, 1, w2).expand(b, 1, h, w2)
+    coords = torch.cat([x - torch.rand(b, 1, h, w2, generator=gen) * (w3 / 4), torch.zeros(b, 1, h, w2)], 1).to(DEV)
+    assert torch.equal(one(coords), two(coords))
+    # on-demand volume of the fused block == the two-step block's
+    assert torch.equal(one.fullcorr, two.fullcorr)
+    # against the fp64 einsum (TF32 tolerance, normwise)
+    ref = torch.einsum("bchw,bchv->bhwv", fl.double(), fr.double()) / math.sqrt(c)
+    if trunc:
+        w2i = torch.arange(w2, device=DEV, dtype=torch.float64).view(1, 1, w2, 1)
+        w3i = torch.arange(w3, device=DEV, dtype=torch.float64).view(1, 1, 1, w3)
+        d, cf = t[0].double().squeeze(1).unsqueeze(-1), t[1].double().squeeze(1).unsqueeze(-1)
+        ref = ref * ((1 - cf) + cf * (torch.sigmoid((w2i - d) - w3i) * (1 - 0.9) + 0.9))
+    assert normwise(one.fullcorr.squeeze(3), ref) < 1e-3

@@ -12,8 +12,8 @@
 //     chunk cc -> scale, x truncation mask -> 16 + 8 + 4 pooled values (levels 1..3)
 // A line q of the packed layout needs L0[8q-4 .. 8q+12] and pooled values of blocks q-4 .. q+5, so step cc
 // can emit the four lines q = 4cc-5 .. 4cc-2 from a register window of the last 44 level-0 values and
-// 24 / 14 / 9 values of levels 1 / 2 / 3 - all indices compile-time constants.  Lines go through a swizzled
-// [128 rows][128 B] staging tile and leave as one TMA store per line index (4-D map {32, line, w2, b*h}: rows
+// 24 / 14 / 9 values of levels 1 / 2 / 3 - all indices compile-time constants.  The four lines go through four
+// swizzled [128 rows][128 B] staging tiles and leave as one TMA store per line index (4-D map {32, line, w2, b*h}: rows
 // beyond W2 are clipped by the map).  Columns outside [0, W3) are zeros (TMA zero fill / virtual chunks),
 // which is exactly the layout's zero padding.
 //
@@ -37,7 +37,7 @@ constexpr int kMaxStages = 6;
 constexpr int kSmemBudget = 224 * 1024;
 constexpr int kThreads = 192;
 constexpr int kEpiWarp0 = 2;
-constexpr int kNStg = 2;                         // [128 rows][128 B] staging tiles for the TMA stores
+constexpr int kNStg = 4;                         // [128 rows][128 B] staging tiles: the four lines of one step
 constexpr int kStagingBytes = kNStg * kBM * 128;
 
 struct Args {
@@ -177,7 +177,7 @@ corr_pack_tf32_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_co
     const int quarter = warp & 3;          // TMEM lane quarter this warp may read
     const int row = quarter * 32 + lane;   // accumulator lane = output row m0 + row
     const int swz = row & 7;
-    uint32_t lt = 0, sc = 0;               // n-tile counter, store counter
+    uint32_t lt = 0;                       // n-tile counter
     for (long long stripe = blockIdx.x; stripe < a.stripes; stripe += gridDim.x) {
       const int tm = (int)(stripe % a.m_tiles);
       const int bh = (int)(stripe / a.m_tiles);
@@ -261,13 +261,14 @@ corr_pack_tf32_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_co
 #pragma unroll
           for (int i = 0; i < 4; ++i) H3[9 + i] = (H2[14 + 2 * i] + H2[14 + 2 * i + 1]) * 0.5f;
         }
+        // ---- the four lines of this step: one staging tile each, one barrier round, four TMA stores
+        if (et == 0) tma_wait_read<0>();                // the previous step's stores have read the tiles
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // (they had this step's TMEM load + pooling to do so)
+        if (live) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int li = 4 * cc + j;  // line index (q + 5)
-          if (li < a.nblk) {
-            uint8_t* tile_s = stag + (sc % kNStg) * (kBM * 128);
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // the store that last used this tile has read it
-            if (live) {
+          for (int j = 0; j < 4; ++j) {
+            if (4 * cc + j < a.nblk) {
+              uint8_t* tile_s = stag + j * (kBM * 128);
               float ln[32];
 #pragma unroll
               for (int s = 0; s < 17; ++s) ln[s] = P[8 * j + s];
@@ -279,15 +280,15 @@ corr_pack_tf32_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_co
                 *reinterpret_cast<float4*>(tile_s + row * 128 + ((k ^ swz) << 4)) =
                     make_float4(ln[4 * k], ln[4 * k + 1], ln[4 * k + 2], ln[4 * k + 3]);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (et == 0) {
-              tma_store_4d(&map_o, tile_s, 0, li, m0, bh);
-              tma_commit();
-              tma_wait_read<kNStg - 1>();
-            }
-            ++sc;
           }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (et == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (4 * cc + j < a.nblk) tma_store_4d(&map_o, stag + j * (kBM * 128), 0, 4 * cc + j, m0, bh);
+          tma_commit();
         }
         if (live) {
 #pragma unroll

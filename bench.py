@@ -229,16 +229,31 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
 
-    gather_buf = torch.empty((world * b, 1, h, w), dtype=torch.float32, device=dev) if dist is not None else None
-    disp_buf = torch.empty((b, 1, h, w), dtype=torch.float32, device=dev)
+    # The path's only collective: gather the quarter-res disparity of every rank.  It is issued
+    # asynchronously (NCCL's own stream, double-buffered) so that step k+1 computes while step k's result
+    # travels; the buffers of step k are reclaimed - i.e. the gather is waited for - at step k+2, and every
+    # outstanding gather is waited for before the closing event of the timed region.
+    gather_bufs = [torch.empty((world * b, 1, h, w), dtype=torch.float32, device=dev) for _ in range(2)] if dist is not None else None
+    disp_bufs = [torch.empty((b, 1, h, w), dtype=torch.float32, device=dev) for _ in range(2)]
+    pending = [None, None]
+    step_no = [0]
 
     def collective(out):
-        # the path's only collective: gather the quarter-res disparity of every rank
         if dist is None:
             return None
-        disp_buf.copy_(out[2][:, :1])
-        dist.all_gather_into_tensor(gather_buf, disp_buf)
-        return gather_buf
+        i = step_no[0] & 1
+        step_no[0] += 1
+        if pending[i] is not None:
+            pending[i].wait()
+        disp_bufs[i].copy_(out[2][:, :1])
+        pending[i] = dist.all_gather_into_tensor(gather_bufs[i], disp_bufs[i], async_op=True)
+        return gather_bufs[i]
+
+    def drain():
+        for i in range(2):
+            if pending[i] is not None:
+                pending[i].wait()
+                pending[i] = None
 
     for _ in range(max(args.warmup, 3)):
         collective(path.step())
@@ -256,6 +271,7 @@ def run_gpu(args):
         for _ in range(2):
             g_build.replay()
             g_look.replay()
+    drain()
     barrier()
     path.launches = 0
     lk_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -271,6 +287,7 @@ def run_gpu(args):
         else:
             out = path.step(lk_events[k])
         collective(out)
+    drain()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -359,7 +376,7 @@ def run_gpu(args):
             "config": {"workload": args.workload, "pairs_per_gpu": b, "C": c, "H4": h, "W4": w, "iters": ITERS,
                        "levels": LEVELS, "radius": RADIUS, "variant": args.variant, "cuda_graph": bool(args.graph),
                        "l2": "inputs+volumes (>1 GB/step) exceed the 126 MB L2; no explicit flush",
-                       "parallelism": f"batch-sharded x{world}, all_gather of quarter-res disparity"},
+                       "parallelism": f"batch-sharded x{world}, async all_gather of quarter-res disparity per step"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(e2e_ms / args.steps, 4), "wall_ms_per_step": round(e2e_wall / args.steps, 4)},
             "gpu_launches": launches,
@@ -381,8 +398,8 @@ def run_gpu(args):
 def run_tiled(args):
     """`--workload c4_middlebury_1984x2872_tiled`: K full-resolution pairs per step, reference tile
     geometry (`--tile-preset`, distinct tiles weighted by multiplicity), every tile runs the whole hot
-    path at its quarter resolution, per-rank cosine-blend accumulation, ONE reduce(sum) of [2,H,W] per
-    image to rank 0.  Path-only: the per-tile disparity is the final lookup coordinate field upsampled
+    path at its quarter resolution, per-rank cosine-blend accumulation, ONE asynchronous reduce(sum) of
+    [images,H,W] per step to rank 0.  Path-only: the per-tile disparity is the final lookup coordinate field upsampled
     x4 (the encoders / GRU that would produce it are out of scope)."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -418,28 +435,64 @@ def run_tiled(args):
         for _ in range(ITERS):
             s, m = B.lookup_pair(fs, fm, coords)
             coords = coords + d["delta"]
-        return (d["coords0"] - coords)[:, :1]  # quarter-res disparity, positive
+        q = (d["coords0"] - coords)[:, :1]  # quarter-res disparity, positive
+        return torch.nn.functional.interpolate(q, scale_factor=4, mode="nearest") * 4.0
+
+    # one tile = ~100 launches of 3-60 us: replay it from a CUDA graph per tile shape (the stitch stays eager)
+    graphs = {}
+    if args.graph:
+        for hw, d in inputs.items():
+            for _ in range(2):
+                tile_path(d)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = tile_path(d)
+            graphs[hw] = (g, out)
+
+    def run_tile(hw):
+        if hw in graphs:
+            graphs[hw][0].replay()
+            return graphs[hw][1]
+        return tile_path(inputs[hw])
+
+    # accumulator [images, H, W] of disp*w, double-buffered: the reduce(sum) of step k runs on NCCL's stream
+    # while step k+1 computes; it is waited for when its buffer comes round again (step k+2) and before the
+    # closing event of the timed region.  The weight plane sum(w) depends on the geometry only: rank 0 forms
+    # it once (tiling.weight_sum) instead of reducing it every step.
+    acc_bufs = [torch.empty(args.images, H, W, device=dev) for _ in range(2)]
+    den = torch.clamp(tiling.weight_sum(H, W, work, device=dev), min=1e-4) if rank == 0 else None
+    pending = [None, None]
+    step_no = [0]
+
+    def finish(i):
+        if pending[i] is not None:
+            if pending[i] != "local":
+                pending[i].wait()
+            pending[i] = None
+            if rank == 0:
+                return acc_bufs[i] / den
+        return None
 
     def step():
-        accs = [torch.zeros(2, H, W, device=dev) for _ in range(args.images)]
+        i = step_no[0] & 1
+        step_no[0] += 1
+        finish(i)
+        accs = acc_bufs[i]
+        accs.zero_()
         for img, (y0, y1, x0, x1), mult in mine:
             pad = tiling.pad_to_32(y1 - y0, x1 - x0)
             hw = ((y1 - y0 + pad[2] + pad[3]) // 4, (x1 - x0 + pad[0] + pad[1]) // 4)
-            q = tile_path(inputs[hw])
-            full = torch.nn.functional.interpolate(q, scale_factor=4, mode="nearest") * 4.0
+            full = run_tile(hw)
             full = full[..., pad[2]: full.shape[-2] - pad[3], pad[0]: full.shape[-1] - pad[1]]
-            key = (y1 - y0, x1 - x0)
+            key = (y1 - y0, x1 - x0, mult)
             if key not in weights:
-                weights[key] = tiling.blend_weight(key[0], key[1], device=dev)
-            wgt = weights[key] * float(mult)
-            accs[img][0, y0:y1, x0:x1] += full[0, 0] * wgt
-            accs[img][1, y0:y1, x0:x1] += wgt
-        outs = []
-        for acc in accs:
-            if dist is not None:
-                dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
-            if rank == 0:
-                outs.append(torch.where(acc[1] > 0, acc[0] / torch.clamp(acc[1], min=1e-4), acc[0]))
+                weights[key] = tiling.blend_weight(key[0], key[1], device=dev) * float(mult)
+            accs[img, y0:y1, x0:x1].addcmul_(full[0, 0], weights[key])
+        pending[i] = dist.reduce(accs, dst=0, op=dist.ReduceOp.SUM, async_op=True) if dist is not None else "local"
+
+    def drain():
+        outs = [finish(i) for i in range(2)]
         return outs
 
     def barrier():
@@ -449,11 +502,13 @@ def run_tiled(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    drain()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
+    drain()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -469,7 +524,8 @@ def run_tiled(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": f"{args.precision} corr, f32 pyramid/lookup",
             "data": "synthetic", "config": {"workload": args.workload, "images_per_step": args.images, "tile_preset": args.tile_preset,
                                            "distinct_tiles_per_image": len(work), "tiles_this_rank": len(mine),
-                                           "parallelism": f"tiles sharded x{world}, reduce(sum) of [2,H,W] per image"},
+                                           "cuda_graph": bool(args.graph),
+                                           "parallelism": f"tiles sharded x{world}, one async reduce(sum) of [images,H,W] per step"},
         }), flush=True)
     if dist is not None:
         dist.barrier()

@@ -14,9 +14,12 @@ MapReduce wrapper so that a tile-sharded run returns the reference's tiled resul
 * blend weight clamp(sin(pi y) sin(pi x), 1e-4) and weighted accumulation - tile_wrapper.py:36-49,
   328-362; final `stitched / clamp(weight, 1e-4)` - tile_wrapper.py:185.
 
-Multi-GPU: tiles are independent units.  Every rank runs its share of tiles, accumulates
-`disp * w` and `w` locally, and ONE collective - `reduce(sum)` of a `[2,H,W]` fp32 tensor to rank 0 -
-stitches the image.  Batch sharding needs one `all_gather` of the disparities.
+Multi-GPU: tiles are independent units.  Every rank runs its share of tiles and accumulates
+`disp * w` locally; ONE collective - `reduce(sum)` of that `[H,W]` fp32 tensor to rank 0 - stitches the
+image.  The weight accumulator `sum w` of the reference depends on the tile geometry
+only, so rank 0 forms it locally (`weight_sum`, same accumulation order as the reference) instead of
+shipping a second `[H,W]` plane through the collective.  Batch sharding needs one `all_gather` of the
+disparities.
 """
 from __future__ import annotations
 
@@ -76,6 +79,20 @@ def blend_weight(h: int, w: int, device=None) -> torch.Tensor:
     wy = torch.sin(torch.pi * y).unsqueeze(1)
     wx = torch.sin(torch.pi * x).unsqueeze(0)
     return torch.clamp(wy * wx, min=1e-4)
+
+
+def weight_sum(height: int, width: int, work, device=None) -> torch.Tensor:
+    """`[H, W]` sum of the blend windows of all tiles in `work` = [(tile, multiplicity)], accumulated in
+    `work` order exactly like the reference's `weight_sum += weight` (tile_wrapper.py:358-362)."""
+    den = torch.zeros(height, width, dtype=torch.float32, device=device)
+    cache = {}
+    for (y0, y1, x0, x1), mult in work:
+        key = (y1 - y0, x1 - x0)
+        if key not in cache:
+            cache[key] = blend_weight(key[0], key[1], device=device)
+        for _ in range(mult):
+            den[y0:y1, x0:x1] += cache[key]
+    return den
 
 
 def pad_to_32(h: int, w: int) -> List[int]:
@@ -142,18 +159,17 @@ def tiled_inference(
         work = tile_multiplicity(height, width, tile_h, tile_w, overlap)
     else:
         work = [(t, 1) for t in enumerate_tiles(height, width, tile_h, tile_w, overlap)]
-    acc = torch.zeros(2, height, width, dtype=torch.float32, device=left.device)  # [disp*w, w]
+    num = torch.zeros(height, width, dtype=torch.float32, device=left.device)  # sum of disp * w over my tiles
     for (y0, y1, x0, x1), mult in shard(work, rank, world):
-        disp = run_tile(model, (left, right, mono_left, mono_right), (y0, y1, x0, x1)).to(acc.device)
-        wgt = blend_weight(y1 - y0, x1 - x0, device=acc.device)
+        disp = run_tile(model, (left, right, mono_left, mono_right), (y0, y1, x0, x1)).to(num.device)
+        wgt = blend_weight(y1 - y0, x1 - x0, device=num.device)
         for _ in range(mult):  # the reference accumulates a repeated tile once per repeat
-            acc[0, y0:y1, x0:x1] += disp[0, 0].float() * wgt
-            acc[1, y0:y1, x0:x1] += wgt
+            num[y0:y1, x0:x1] += disp[0, 0].float() * wgt
     if world > 1:
-        dist.reduce(acc, dst=dst, op=dist.ReduceOp.SUM, group=group)  # the path's only collective
+        dist.reduce(num, dst=dst, op=dist.ReduceOp.SUM, group=group)  # the path's only collective
         if rank != dst:
             return None
-    num, den = acc[0], acc[1]
+    den = weight_sum(height, width, work, device=num.device)  # geometry only: no need to communicate it
     out = torch.where(den > 0, num / torch.clamp(den, min=1e-4), num)
     return out.view(1, 1, height, width)
 

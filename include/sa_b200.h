@@ -148,6 +148,20 @@ int sa_lookup_packed_conv(const float* packed_a, const float* packed_b, int W3, 
                           int64_t coords_bstride, const float* weight, const float* bias, float* out_a, float* out_b,
                           int B, int H, int W, void* stream);
 
+/* ---------------------------------------------------------------- soft-argmax / entropy reductions
+ * The four reductions the model runs over the aggregated mono volume (stereoanywhere.py:174-177), two per
+ * launch with ONE read of the volume (the reference makes four separate softmax passes).  vol is
+ * [BH = B*H][W2][W3] fp32 contiguous (the [B,1,H,W2,W3] tensor).
+ *   sa_volume_softargmax:   disp_left [BH,W2] = w2 - sum_w3 softmax_w3(vol) * w3   (utils/utils.py:112-131)
+ *                           disp_right[BH,W3] = sum_w2 softmax_w2(vol) * w2 - w3   (utils/utils.py:133-152)
+ *   sa_volume_entropy_conf: conf_left [BH,W2] = 1 + sum_w3 p*log2(p+1e-6)/log2(W3) (utils/utils.py:154-161)
+ *                           conf_right[BH,W3] = 1 + sum_w2 p*log2(p+1e-6)/log2(W2) (utils/utils.py:163-170)
+ * W3 <= 1024.  Agreement with the reference's fp32 ATen sequence: <= 2e-4 px / <= 2e-5 (tests). */
+int sa_volume_softargmax(const float* vol, int64_t BH, int W2, int W3, float* disp_left, float* disp_right,
+                         void* stream);
+int sa_volume_entropy_conf(const float* vol, int64_t BH, int W2, int W3, float* conf_left, float* conf_right,
+                           void* stream);
+
 /* ---------------------------------------------------------------- A5: truncation mask (standalone)
  * mask[b,h,w2,w3] = (1-c) + c * (sigmoid((w2 - d) - w3) * (1-g) + g); writes `out` = mask * vol
  * when vol != NULL, else the mask itself.  Replaces `truncate_corr_volume_v2`

@@ -277,6 +277,64 @@ class OracleCorrBlock:
     corr = staticmethod(aten_corr_volume)
 
 
+# --------------------------------------------------------------------------------------
+# SURVEY 8f-2 - soft-argmax disparities / entropy confidences of an aggregated volume
+# --------------------------------------------------------------------------------------
+
+
+def aten_estimate_left_disparity(vol: torch.Tensor, vol_pad: Sequence[int] = (0, 0)) -> torch.Tensor:
+    """x - E_{softmax over w3}[w3], `[B,1,H,W2]` (utils/utils.py:112-131; called at stereoanywhere.py:174)."""
+    b, _, h, w2, w3 = vol.shape
+    idx = torch.arange(0, w3, dtype=vol.dtype).view(1, 1, 1, -1).repeat(b, 1, 1, 1)
+    prob = F.softmax(vol.squeeze(1) * 1.0, dim=3)
+    expect = torch.sum(prob * idx, 3, keepdim=False)
+    xs = torch.arange(w2, dtype=vol.dtype).view(1, 1, w2).repeat(b, h, 1)
+    return (xs - expect).unsqueeze(1)[:, :, :, vol_pad[0]: w2 - vol_pad[1]]
+
+
+def aten_estimate_right_disparity(vol: torch.Tensor, vol_pad: Sequence[int] = (0, 0)) -> torch.Tensor:
+    """E_{softmax over w2}[w2] - x, `[B,1,H,W3]` (utils/utils.py:133-152; stereoanywhere.py:175)."""
+    b, _, h, w2, w3 = vol.shape
+    idx = torch.arange(0, w2, dtype=vol.dtype).view(1, 1, -1, 1).repeat(b, 1, 1, 1)
+    prob = F.softmax(vol.squeeze(1) * 1.0, dim=2)
+    expect = torch.sum(prob * idx, 2, keepdim=False)
+    xs = torch.arange(w3, dtype=vol.dtype).view(1, 1, w3).repeat(b, h, 1)
+    return (expect - xs).unsqueeze(1)[:, :, :, vol_pad[0]: w3 - vol_pad[1]]
+
+
+def aten_estimate_left_confidence(vol: torch.Tensor) -> torch.Tensor:
+    """1 - H(softmax over w3) / log2(W3), `[B,1,H,W2]` (utils/utils.py:154-161; stereoanywhere.py:176)."""
+    w3 = vol.shape[4]
+    prob = F.softmax(vol.squeeze(1), dim=3)
+    ent = -torch.sum(prob * torch.log2(prob + 1e-6), dim=3, keepdim=False) / math.log2(w3)
+    return (1 - ent).unsqueeze(1)
+
+
+def aten_estimate_right_confidence(vol: torch.Tensor) -> torch.Tensor:
+    """1 - H(softmax over w2) / log2(W2), `[B,1,H,W3]` (utils/utils.py:163-170; stereoanywhere.py:177)."""
+    w2 = vol.shape[3]
+    prob = F.softmax(vol.squeeze(1), dim=2)
+    ent = -torch.sum(prob * torch.log2(prob + 1e-6), dim=2, keepdim=False) / math.log2(w2)
+    return (1 - ent).unsqueeze(1)
+
+
+def closed_volume_reductions(vol: np.ndarray):
+    """float64 closed forms of the four reductions; vol [B,1,H,W2,W3] -> (dl, dr, cl, cr)."""
+    v = vol.astype(np.float64)[:, 0]
+    b, h, w2, w3 = v.shape
+
+    def softmax(x, axis):
+        e = np.exp(x - x.max(axis=axis, keepdims=True))
+        return e / e.sum(axis=axis, keepdims=True)
+
+    p3, p2 = softmax(v, 3), softmax(v, 2)
+    dl = np.arange(w2).reshape(1, 1, w2) - (p3 * np.arange(w3).reshape(1, 1, 1, w3)).sum(3)
+    dr = (p2 * np.arange(w2).reshape(1, 1, w2, 1)).sum(2) - np.arange(w3).reshape(1, 1, w3)
+    cl = 1 + (p3 * np.log2(p3 + 1e-6)).sum(3) / math.log2(w3)
+    cr = 1 + (p2 * np.log2(p2 + 1e-6)).sum(2) / math.log2(w2)
+    return dl[:, None], dr[:, None], cl[:, None], cr[:, None]
+
+
 def run_path_cpu(
     fmap_l: torch.Tensor,
     fmap_r: torch.Tensor,

@@ -26,7 +26,22 @@ from .corr import (  # noqa: E402
     truncation_mask,
 )
 
+from .reductions import (  # noqa: E402
+    estimate_confidences,
+    estimate_disparities,
+    estimate_left_confidence,
+    estimate_left_disparity,
+    estimate_right_confidence,
+    estimate_right_disparity,
+)
+
 __all__ = [
+    "estimate_disparities",
+    "estimate_confidences",
+    "estimate_left_disparity",
+    "estimate_right_disparity",
+    "estimate_left_confidence",
+    "estimate_right_confidence",
     "CorrBlockB200",
     "truncation_mask",
     "masked_volume",

@@ -287,6 +287,32 @@ def corr_packable(c: int, w2: int, w3: int) -> bool:
     return c % 32 == 0 and c >= 32 and w2 % 4 == 0 and w3 >= 8 and w3 % 8 == 0
 
 
+def _volume_reduce(vol: torch.Tensor, which: str):
+    """[B,1,H,W2,W3] -> (left [B,1,H,W2], right [B,1,H,W3]); `which` = "softargmax" | "entropy_conf"
+    (csrc/volume_reduce.cu: one read of the volume for both directions)."""
+    _cuda_f32(vol, "corr_volume")
+    _req(vol.dim() == 5 and vol.shape[1] == 1, "corr_volume must be [B,1,H,W2,W3]")
+    b, _, h, w2, w3 = vol.shape
+    _req(w3 <= 1024, "W3 > 1024 is not covered by the reduction kernels")
+    vol = vol.contiguous()
+    left = torch.empty((b, 1, h, w2), dtype=torch.float32, device=vol.device)
+    right = torch.empty((b, 1, h, w3), dtype=torch.float32, device=vol.device)
+    lib = _lib.load()
+    fn = lib.sa_volume_softargmax if which == "softargmax" else lib.sa_volume_entropy_conf
+    with _on(vol.device):
+        rc = fn(vol.data_ptr(), b * h, w2, w3, left.data_ptr(), right.data_ptr(), _stream_ptr(vol))
+    _lib.check(rc, f"sa_volume_{which}")
+    return left, right
+
+
+def _volume_softargmax(vol: torch.Tensor):
+    return _volume_reduce(vol, "softargmax")
+
+
+def _volume_entropy_conf(vol: torch.Tensor):
+    return _volume_reduce(vol, "entropy_conf")
+
+
 def _lookup_packed(packed_a: torch.Tensor, packed_b: Optional[torch.Tensor], w3: int, coords: torch.Tensor):
     coords, b, h, w = _coords_view(coords)
     _cuda_f32(packed_a, "packed pyramid")
@@ -426,6 +452,8 @@ _LIBDEF.define("lookup2(Tensor[] levels_a, Tensor[] levels_b, int[] widths, Tens
 _LIBDEF.define("pack_pyramid(Tensor vol_rows, Tensor? trunc_disp, Tensor? trunc_conf, float trunc_gain) -> Tensor")
 _LIBDEF.define("pack_pyramid_normals(Tensor normals_l, Tensor normals_r, float post_scale) -> Tensor")
 _LIBDEF.define("corr_pack(Tensor fmap_l, Tensor fmap_r, Tensor? trunc_disp, Tensor? trunc_conf, float trunc_gain) -> Tensor")
+_LIBDEF.define("volume_softargmax(Tensor vol) -> (Tensor, Tensor)")
+_LIBDEF.define("volume_entropy_conf(Tensor vol) -> (Tensor, Tensor)")
 _LIBDEF.define("lookup_packed(Tensor packed, int w3, Tensor coords) -> Tensor")
 _LIBDEF.define("lookup_packed2(Tensor packed_a, Tensor packed_b, int w3, Tensor coords) -> (Tensor, Tensor)")
 _LIBDEF.define("lookup_packed_conv(Tensor packed_a, Tensor packed_b, int w3, Tensor coords, Tensor weight, Tensor bias) -> (Tensor, Tensor)")
@@ -440,6 +468,8 @@ _LIBDEF.impl("lookup2", _lookup2, "CUDA")
 _LIBDEF.impl("pack_pyramid", _pack_pyramid, "CUDA")
 _LIBDEF.impl("pack_pyramid_normals", _pack_pyramid_normals, "CUDA")
 _LIBDEF.impl("corr_pack", _corr_pack, "CUDA")
+_LIBDEF.impl("volume_softargmax", _volume_softargmax, "CUDA")
+_LIBDEF.impl("volume_entropy_conf", _volume_entropy_conf, "CUDA")
 _LIBDEF.impl("lookup_packed", _lookup_packed1, "CUDA")
 _LIBDEF.impl("lookup_packed2", _lookup_packed2, "CUDA")
 _LIBDEF.impl("lookup_packed_conv", _lookup_packed_conv, "CUDA")
@@ -447,5 +477,5 @@ _LIBDEF.impl("truncate", _truncate, "CUDA")
 _LIBDEF.impl("masked_volume", _masked_volume, "CUDA")
 _LIBDEF.impl("corrupt", _corrupt, "CUDA")
 
-OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "corr_pack", "lookup_packed", "lookup_packed2", "lookup_packed_conv",
+OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "corr_pack", "volume_softargmax", "volume_entropy_conf", "lookup_packed", "lookup_packed2", "lookup_packed_conv",
             "truncate", "masked_volume", "corrupt"]

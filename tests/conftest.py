@@ -49,3 +49,8 @@ def golden_model():
 @pytest.fixture(scope="session")
 def golden_tiles():
     return dict(np.load(os.path.join(GOLDEN, "tiles.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_reductions():
+    return dict(np.load(os.path.join(GOLDEN, "reductions.npz")))

@@ -239,8 +239,27 @@ def tiles():
     print("tiles.npz", sum(np.asarray(v).nbytes for v in out.values()) / 1e6, "MB raw")
 
 
+def reductions():
+    """the reference's four soft-argmax / entropy reductions (utils/utils.py:112-170)."""
+    _, U = ref_shim.import_reference_corr()
+    g = torch.Generator().manual_seed(4321)
+    out = {}
+    for tag, shape, gain in [("sq24", (2, 1, 3, 24, 24), 3.0), ("r40x50", (1, 1, 2, 40, 50), 6.0), ("flat33", (1, 1, 2, 33, 33), 0.05)]:
+        v = torch.randn(*shape, generator=g) * gain
+        out[f"{tag}_vol"] = _np(v)
+        out[f"{tag}_dl"] = _np(U.estimate_left_disparity(v))
+        out[f"{tag}_dr"] = _np(U.estimate_right_disparity(v))
+        out[f"{tag}_cl"] = _np(U.estimate_left_confidence(v))
+        out[f"{tag}_cr"] = _np(U.estimate_right_confidence(v))
+    v = torch.from_numpy(out["sq24_vol"])
+    out["sq24_dl_pad"] = _np(U.estimate_left_disparity(v, vol_pad=[2, 3]))
+    out["sq24_dr_pad"] = _np(U.estimate_right_disparity(v, vol_pad=[2, 3]))
+    np.savez_compressed(os.path.join(HERE, "reductions.npz"), **out)
+    print("reductions.npz", sum(np.asarray(v).nbytes for v in out.values()) / 1e6, "MB raw")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    path_small()
-    model_slice()
-    tiles()
+    which = sys.argv[1:] or ["path_small", "model_slice", "tiles", "reductions"]
+    for name in which:
+        {"path_small": path_small, "model_slice": model_slice, "tiles": tiles, "reductions": reductions}[name]()

@@ -420,3 +420,58 @@ def test_corr_pack_fused_matches_two_step(sa, shape, trunc):
         d, cf = t[0].double().squeeze(1).unsqueeze(-1), t[1].double().squeeze(1).unsqueeze(-1)
         ref = ref * ((1 - cf) + cf * (torch.sigmoid((w2i - d) - w3i) * (1 - 0.9) + 0.9))
     assert normwise(one.fullcorr.squeeze(3), ref) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------ 8f-2 reductions
+@pytest.mark.parametrize("tag", ["sq24", "r40x50", "flat33"])
+def test_golden_volume_reductions(sa, golden_reductions, tag):
+    """Soft-argmax disparities / entropy confidences vs the reference's own outputs (fixtures)."""
+    g = golden_reductions
+    v = G(g[f"{tag}_vol"])
+    dl, dr = sa.estimate_disparities(v)
+    cl, cr = sa.estimate_confidences(v)
+    assert dl.shape == g[f"{tag}_dl"].shape and dr.shape == g[f"{tag}_dr"].shape
+    assert maxabs(dl, g[f"{tag}_dl"]) < 2e-4 and maxabs(dr, g[f"{tag}_dr"]) < 2e-4   # pixels
+    assert maxabs(cl, g[f"{tag}_cl"]) < 2e-5 and maxabs(cr, g[f"{tag}_cr"]) < 2e-5
+    if tag == "sq24":
+        assert maxabs(sa.estimate_left_disparity(v, vol_pad=[2, 3]), g["sq24_dl_pad"]) < 2e-4
+        assert maxabs(sa.estimate_right_disparity(v, vol_pad=[2, 3]), g["sq24_dr_pad"]) < 2e-4
+        assert torch.equal(sa.estimate_left_confidence(v), cl) and torch.equal(sa.estimate_right_confidence(v), cr)
+
+
+@pytest.mark.parametrize("shape,gain", [((2, 1, 5, 312, 312), 4.0), ((1, 1, 3, 240, 240), 1.0), ((1, 1, 2, 130, 37), 8.0),
+                                        ((1, 1, 2, 37, 130), 8.0), ((1, 1, 1, 768, 768), 2.0), ((1, 1, 2, 5, 3), 1.0)])
+def test_volume_reductions_vs_oracle(sa, shape, gain):
+    """Seeded volumes at model-like and awkward shapes vs the oracle (ATen fp32 op sequence and fp64 closed form)."""
+    gen = torch.Generator().manual_seed(77 + shape[3])
+    v = torch.randn(*shape, generator=gen) * gain
+    dl, dr = sa.estimate_disparities(v.to(DEV))
+    cl, cr = sa.estimate_confidences(v.to(DEV))
+    w = max(shape[3], shape[4])
+    assert maxabs(dl, O.aten_estimate_left_disparity(v)) < 1e-6 * w * 2 and maxabs(dr, O.aten_estimate_right_disparity(v)) < 1e-6 * w * 2
+    assert maxabs(cl, O.aten_estimate_left_confidence(v)) < 3e-5 and maxabs(cr, O.aten_estimate_right_confidence(v)) < 3e-5
+    rdl, rdr, rcl, rcr = O.closed_volume_reductions(v.numpy())
+    assert maxabs(dl, rdl) < 1e-6 * w * 2 and maxabs(dr, rdr) < 1e-6 * w * 2
+    assert maxabs(cl, rcl) < 3e-5 and maxabs(cr, rcr) < 3e-5
+
+
+def test_volume_reductions_properties_full_size(sa):
+    """c2-size volume: a one-hot-like volume recovers its own disparity; a constant volume gives the uniform
+    expectation and zero confidence (size-independent properties)."""
+    b, h, w = 2, 96, 312
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    d = torch.randint(0, 40, (b, h, w), device=DEV, generator=gen)
+    x = torch.arange(w, device=DEV).view(1, 1, w)
+    tgt = (x - d).clamp(min=0)                                   # matching column of every left pixel
+    vol = torch.full((b, 1, h, w, w), -40.0, device=DEV)
+    vol[:, 0].scatter_(3, tgt.unsqueeze(3), 40.0)
+    dl, _ = sa.estimate_disparities(vol)
+    assert float((dl[:, 0] - (x - tgt).float()).abs().max()) < 1e-3
+    cl, _ = sa.estimate_confidences(vol)
+    assert float(cl.min()) > 0.999
+    flat = torch.zeros(1, 1, 4, w, w, device=DEV)
+    dl, dr = sa.estimate_disparities(flat)
+    assert float((dl[0, 0, 0] - (torch.arange(w, device=DEV) - (w - 1) / 2)).abs().max()) < 1e-3
+    assert float((dr[0, 0, 0] - ((w - 1) / 2 - torch.arange(w, device=DEV))).abs().max()) < 1e-3
+    cl, cr = sa.estimate_confidences(flat)
+    assert float(cl.abs().max()) < 2e-3 and float(cr.abs().max()) < 2e-3  # log2(1/W + 1e-6) is not exactly -log2 W

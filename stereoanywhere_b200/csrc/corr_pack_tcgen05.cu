@@ -22,7 +22,7 @@
 // HBM: reads 2*B*C*H*W*4, writes B*H*W2*(W3/8+9)*128; bound by the packed write.
 #include <cuda.h>
 
-#include "sa_common.cuh"
+#include "pack_stream.cuh"
 #include "tc_common.cuh"
 
 namespace sa {
@@ -54,12 +54,6 @@ struct Args {
   const float* conf;
   float gain, one_minus_gain;
 };
-
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
-               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
 
 template <bool TRUNC>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -191,20 +185,8 @@ corr_pack_tf32_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_co
         omc = 1.0f - tc;
         centre = (float)w2 - __ldg(a.disp + r);
       }
-      // register windows (relative to the chunk of the current step cc):
-      //   P [i] = L0[32cc - 44 + i]   i < 44
-      //   H1[i] = L1[16cc - 24 + i]   i < 40 (24.. are this step's)
-      //   H2[i] = L2[ 8cc - 14 + i]   i < 22 (14..)
-      //   H3[i] = L3[ 4cc -  9 + i]   i < 13 ( 9..)
-      float P[44], H1[40], H2[22], H3[13];
-#pragma unroll
-      for (int i = 0; i < 44; ++i) P[i] = 0.f;
-#pragma unroll
-      for (int i = 0; i < 24; ++i) H1[i] = 0.f;
-#pragma unroll
-      for (int i = 0; i < 14; ++i) H2[i] = 0.f;
-#pragma unroll
-      for (int i = 0; i < 9; ++i) H3[i] = 0.f;
+      PackWindow win;  // register window of the streaming packer (pack_stream.cuh)
+      win.reset();
       int tn = 0, wi = 0;  // n-tile / chunk-in-tile of the current chunk
       for (int cc = 0; cc < a.n_steps; ++cc) {
         float v[32];
@@ -253,34 +235,16 @@ corr_pack_tf32_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_co
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        if (live) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) H1[24 + i] = (v[2 * i] + v[2 * i + 1]) * 0.5f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) H2[14 + i] = (H1[24 + 2 * i] + H1[24 + 2 * i + 1]) * 0.5f;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) H3[9 + i] = (H2[14 + 2 * i] + H2[14 + 2 * i + 1]) * 0.5f;
-        }
+        if (live) win.pool(v);
         // ---- the four lines of this step: one staging tile each, one barrier round, four TMA stores
         if (et == 0) tma_wait_read<0>();                // the previous step's stores have read the tiles
         asm volatile("bar.sync 1, 128;" ::: "memory");  // (they had this step's TMEM load + pooling to do so)
         if (live) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (4 * cc + j < a.nblk) {
-              uint8_t* tile_s = stag + j * (kBM * 128);
-              float ln[32];
-#pragma unroll
-              for (int s = 0; s < 17; ++s) ln[s] = P[8 * j + s];
-              ln[17] = H1[4 * j]; ln[18] = H1[4 * j + 1]; ln[19] = H1[4 * j + 10]; ln[20] = H1[4 * j + 11]; ln[21] = H1[4 * j + 12];
-              ln[22] = H2[2 * j]; ln[23] = H2[2 * j + 1]; ln[24] = H2[2 * j + 8]; ln[25] = H2[2 * j + 9]; ln[26] = H2[2 * j + 10];
-              ln[27] = H3[j]; ln[28] = H3[j + 1]; ln[29] = H3[j + 7]; ln[30] = H3[j + 8]; ln[31] = H3[j + 9];
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                *reinterpret_cast<float4*>(tile_s + row * 128 + ((k ^ swz) << 4)) =
-                    make_float4(ln[4 * k], ln[4 * k + 1], ln[4 * k + 2], ln[4 * k + 3]);
-            }
-          }
+          const int li = 4 * cc;
+          if (li + 0 < a.nblk) win.store_line<0>(stag + 0 * (kBM * 128) + row * 128, swz);
+          if (li + 1 < a.nblk) win.store_line<1>(stag + 1 * (kBM * 128) + row * 128, swz);
+          if (li + 2 < a.nblk) win.store_line<2>(stag + 2 * (kBM * 128) + row * 128, swz);
+          if (li + 3 < a.nblk) win.store_line<3>(stag + 3 * (kBM * 128) + row * 128, swz);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -290,18 +254,7 @@ corr_pack_tf32_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_co
             if (4 * cc + j < a.nblk) tma_store_4d(&map_o, stag + j * (kBM * 128), 0, 4 * cc + j, m0, bh);
           tma_commit();
         }
-        if (live) {
-#pragma unroll
-          for (int i = 0; i < 12; ++i) P[i] = P[32 + i];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) P[12 + i] = v[i];
-#pragma unroll
-          for (int i = 0; i < 24; ++i) H1[i] = H1[16 + i];
-#pragma unroll
-          for (int i = 0; i < 14; ++i) H2[i] = H2[8 + i];
-#pragma unroll
-          for (int i = 0; i < 9; ++i) H3[i] = H3[4 + i];
-        }
+        if (live) win.advance(v);
       }
       lt += (uint32_t)a.n_tiles;
     }

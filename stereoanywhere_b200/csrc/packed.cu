@@ -62,7 +62,7 @@ struct PackArgs {
 constexpr int kPackMaxV4 = 3;  // float4 per lane and row held in registers while prefetching (W <= 384)
 
 template <bool TRUNC, bool NORMALS>
-__global__ void __launch_bounds__(256, 3) pack_kernel(const PackArgs a) {
+__global__ void __launch_bounds__(256, NORMALS ? 2 : 3) pack_kernel(const PackArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int W = a.W;
   const int W4 = W >> 2;
@@ -82,14 +82,24 @@ __global__ void __launch_bounds__(256, 3) pack_kernel(const PackArgs a) {
   }
   const bool prefetch = !NORMALS && (W4 <= 32 * kPackMaxV4);
   const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
-  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const long long gwarp = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  // Volume source: rows round-robin over the warps (the next row is prefetched while this one is packed).
+  // Normals source: a CONTIGUOUS chunk of rows per warp, so that the right normals of the image row (b,h) - the
+  // same for all its W2 volume rows - stay in registers and only three scalars change from row to row.
+  const bool resident = NORMALS && (W4 <= 32 * kPackMaxV4);
+  const long long rows_per_warp = (a.rows + warps_total - 1) / warps_total;
+  long long row = NORMALS ? gwarp * rows_per_warp : gwarp;
+  const long long row_end = NORMALS ? min(a.rows, row + rows_per_warp) : a.rows;
+  const long long row_step = NORMALS ? 1 : warps_total;
   float4 nxt[kPackMaxV4];
-  if (prefetch && row < a.rows) {
+  float4 rr0[kPackMaxV4], rr1[kPackMaxV4], rr2[kPackMaxV4];
+  long long cur_bh = -1;
+  if (prefetch && row < row_end) {
 #pragma unroll
     for (int i = 0; i < kPackMaxV4; ++i)
       if (lane + 32 * i < W4) nxt[i] = ld_stream_v4(a.src + row * W + 4 * (lane + 32 * i));
   }
-  for (; row < a.rows; row += warps_total) {
+  for (; row < row_end; row += row_step) {
     float c = 0.f, centre = 0.f, omc = 1.f;
     if (TRUNC) {
       c = __ldg(a.conf + row);
@@ -108,6 +118,17 @@ __global__ void __launch_bounds__(256, 3) pack_kernel(const PackArgs a) {
       const float* nlp = a.nl + (b * 3 * a.H + h) * a.W2 + w2;
       n0 = __ldg(nlp); n1 = __ldg(nlp + plane2); n2 = __ldg(nlp + 2 * plane2);
       nrp = a.nr + (b * 3 * a.H + h) * (long long)W;
+      if (resident && bh != cur_bh) {
+        cur_bh = bh;
+#pragma unroll
+        for (int i = 0; i < kPackMaxV4; ++i) {
+          if (lane + 32 * i < W4) {
+            rr0[i] = __ldg(reinterpret_cast<const float4*>(nrp + 4 * (lane + 32 * i)));
+            rr1[i] = __ldg(reinterpret_cast<const float4*>(nrp + plane3 + 4 * (lane + 32 * i)));
+            rr2[i] = __ldg(reinterpret_cast<const float4*>(nrp + 2 * plane3 + 4 * (lane + 32 * i)));
+          }
+        }
+      }
     }
     auto put_row = [&](int v, float4 q) {
       if (TRUNC) {
@@ -116,24 +137,31 @@ __global__ void __launch_bounds__(256, 3) pack_kernel(const PackArgs a) {
       *reinterpret_cast<float4*>(s0 + 4 * v) = q;
       *reinterpret_cast<float2*>(s1 + 2 * v) = make_float2((q.x + q.y) * 0.5f, (q.z + q.w) * 0.5f);
     };
-    if (NORMALS) {
+    auto mono4 = [&](const float4& r0, const float4& r1, const float4& r2) {
+      float4 q;
+      q.x = div_const(fmaf(n2, r2.x, fmaf(n1, r1.x, fmaf(n0, r0.x, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
+      q.y = div_const(fmaf(n2, r2.y, fmaf(n1, r1.y, fmaf(n0, r0.y, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
+      q.z = div_const(fmaf(n2, r2.z, fmaf(n1, r1.z, fmaf(n0, r0.z, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
+      q.w = div_const(fmaf(n2, r2.w, fmaf(n1, r1.w, fmaf(n0, r0.w, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
+      return q;
+    };
+    if (NORMALS && resident) {
+#pragma unroll
+      for (int i = 0; i < kPackMaxV4; ++i)
+        if (lane + 32 * i < W4) put_row(lane + 32 * i, mono4(rr0[i], rr1[i], rr2[i]));
+    } else if (NORMALS) {
       for (int v = lane; v < W4; v += 32) {
         const float4 r0 = __ldg(reinterpret_cast<const float4*>(nrp + 4 * v));
         const float4 r1 = __ldg(reinterpret_cast<const float4*>(nrp + plane3 + 4 * v));
         const float4 r2 = __ldg(reinterpret_cast<const float4*>(nrp + 2 * plane3 + 4 * v));
-        float4 q;
-        q.x = div_const(fmaf(n2, r2.x, fmaf(n1, r1.x, fmaf(n0, r0.x, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
-        q.y = div_const(fmaf(n2, r2.y, fmaf(n1, r1.y, fmaf(n0, r0.y, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
-        q.z = div_const(fmaf(n2, r2.z, fmaf(n1, r1.z, fmaf(n0, r0.z, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
-        q.w = div_const(fmaf(n2, r2.w, fmaf(n1, r1.w, fmaf(n0, r0.w, 0.f))), a.divisor, a.inv_divisor) * a.post_scale;
-        put_row(v, q);
+        put_row(v, mono4(r0, r1, r2));
       }
     } else if (prefetch) {
 #pragma unroll
       for (int i = 0; i < kPackMaxV4; ++i)
         if (lane + 32 * i < W4) put_row(lane + 32 * i, nxt[i]);
       const long long nrow = row + warps_total;  // the next row's loads fly while this row is packed
-      if (nrow < a.rows) {
+      if (nrow < row_end) {
 #pragma unroll
         for (int i = 0; i < kPackMaxV4; ++i)
           if (lane + 32 * i < W4) nxt[i] = ld_stream_v4(a.src + nrow * W + 4 * (lane + 32 * i));

@@ -475,3 +475,20 @@ def test_volume_reductions_properties_full_size(sa):
     assert float((dr[0, 0, 0] - ((w - 1) / 2 - torch.arange(w, device=DEV))).abs().max()) < 1e-3
     cl, cr = sa.estimate_confidences(flat)
     assert float(cl.abs().max()) < 2e-3 and float(cr.abs().max()) < 2e-3  # log2(1/W + 1e-6) is not exactly -log2 W
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 312, 312), (1, 3, 128, 128), (1, 2, 40, 40), (1, 2, 132, 264), (1, 1, 520, 776), (1, 2, 8, 8)])
+def test_pack_normals_matches_two_step(sa, shape):
+    """The mono packer (pack_kernel<normals>, behind from_normals; right normals register-resident over a
+    contiguous chunk of rows) vs mono_corr + pack: identical bit for bit (C = 3 FMA order shared with sa_corr_fp32)."""
+    b, h, w2, w3 = shape
+    gen = torch.Generator().manual_seed(41 + w3)
+    nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w2, generator=gen), dim=1).to(DEV)
+    nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w3, generator=gen), dim=1).to(DEV)
+    B = sa.CorrBlockB200
+    fused = B.from_normals(nl, nr)
+    two = B(B.mono_corr(nl, nr))
+    assert fused._packed is not None and torch.equal(fused._packed, two._packed)
+    x = torch.arange(w2, dtype=torch.float32).view(1, 1, 1, w2).expand(b, 1, h, w2)
+    coords = torch.cat([x - torch.rand(b, 1, h, w2, generator=gen) * (w3 / 4), torch.zeros(b, 1, h, w2)], 1).to(DEV)
+    assert torch.equal(fused(coords), two(coords))

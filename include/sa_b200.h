@@ -162,6 +162,23 @@ int sa_volume_softargmax(const float* vol, int64_t BH, int W2, int W3, float* di
 int sa_volume_entropy_conf(const float* vol, int64_t BH, int W2, int W3, float* conf_left, float* conf_right,
                            void* stream);
 
+/* ---------------------------------------------------------------- backward of lookup and pyramid
+ * Adjoints of sa_lookup / sa_pyramid for the reference's training step (train.py:277,383: autograd through
+ * grid_sample and avg_pool2d).  Coordinates are detached before every lookup (stereoanywhere.py:268), so only
+ * the volume receives a gradient.
+ *   sa_lookup_backward   h_dlevels[i][row, c] += adjoint of the taps of level i for grad_out [B, L*(2r+1), H, W]
+ *                        (same coords / pad0 as the forward call; level-gradient buffers are rows x pitch_i
+ *                        floats, zero-initialised by the caller, accumulated over the GRU iterations)
+ *   sa_pyramid_backward  folds the level gradients into level 0 in place: d0 <- [T *] (dP_0 + pooled adjoints);
+ *                        with trunc_* the result is the gradient w.r.t. V of the block built from T * V
+ *                        (T detached as in the reference, stereoanywhere.py:203). */
+int sa_lookup_backward(const float* grad_out, const float* coords, int64_t coords_bstride, float* const* h_dlevels,
+                       const int* h_widths, const int64_t* h_pitches, int num_levels, int radius, int B, int H, int W,
+                       int pad0, void* stream);
+int sa_pyramid_backward(float* d0, const float* const* h_dlevels, const int* h_widths, const int64_t* h_pitches,
+                        int num_levels, int64_t rows, const float* trunc_disp, const float* trunc_conf, double trunc_gain,
+                        int w2_size, void* stream);
+
 /* ---------------------------------------------------------------- A5: truncation mask (standalone)
  * mask[b,h,w2,w3] = (1-c) + c * (sigmoid((w2 - d) - w3) * (1-g) + g); writes `out` = mask * vol
  * when vol != NULL, else the mask itself.  Replaces `truncate_corr_volume_v2`

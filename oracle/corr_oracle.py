@@ -278,6 +278,42 @@ class OracleCorrBlock:
 
 
 # --------------------------------------------------------------------------------------
+# SURVEY 8f-4 - closed-form adjoint of lookup + pyramid (what autograd computes through
+# grid_sample / avg_pool2d in the reference's training step, train.py:277,383)
+# --------------------------------------------------------------------------------------
+
+
+def closed_lookup_backward(vol_shape, coords_list, weights_list, num_levels: int = 4, radius: int = 4) -> np.ndarray:
+    """d/dV of sum_k <lookup(V, coords_k), weights_k> in float64; returns [B,H,W2,W3].
+
+    Lookup taps (corr.py:93-115): out[b, i*(2r+1)+k] = (1-f) P_i[x0+k-r] + f P_i[x0+k-r+1] with zero padding; the
+    pyramid is P_{i+1}[j] = 0.5 (P_i[2j] + P_i[2j+1]) (corr.py:88-91), so dP_i[m] += 0.5 dP_{i+1}[m >> 1]."""
+    b, h, w2, _, w3 = vol_shape
+    widths = [w3]
+    for _ in range(num_levels - 1):
+        widths.append(widths[-1] // 2)
+    dl = [np.zeros((b, h, w2, w), dtype=np.float64) for w in widths]
+    nt = 2 * radius + 1
+    for coords, wts in zip(coords_list, weights_list):
+        x = coords[:, 0].astype(np.float64)                     # [B,H,W2]
+        for i, w in enumerate(widths):
+            xs = x / (2 ** i)
+            x0 = np.floor(xs)
+            f = xs - x0
+            for k in range(nt):
+                g = wts[:, i * nt + k].astype(np.float64)       # [B,H,W2]
+                for off, wgt in ((0, 1.0 - f), (1, f)):
+                    c = (x0 + k - radius + off).astype(np.int64)
+                    ok = (c >= 0) & (c < w)
+                    bi, hi, wi = np.nonzero(ok)
+                    np.add.at(dl[i], (bi, hi, wi, c[ok]), (wgt * g)[ok])
+    for i in range(num_levels - 1, 0, -1):
+        n = widths[i]
+        dl[i - 1][..., : 2 * n] += 0.5 * np.repeat(dl[i], 2, axis=-1)
+    return dl[0]
+
+
+# --------------------------------------------------------------------------------------
 # SURVEY 8f-2 - soft-argmax disparities / entropy confidences of an aggregated volume
 # --------------------------------------------------------------------------------------
 

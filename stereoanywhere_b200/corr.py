@@ -8,8 +8,11 @@ reference model by adding one branch at stereoanywhere.py:128-133 (see INTEGRATI
     elif self.args.corr_implementation == "b200":
         corr_block = CorrBlockB200
 
-All arithmetic runs in the sm_100a kernels behind `torch.ops.sa_b200.*`; there is no CPU path
-and no autograd (the block raises under `requires_grad`).
+All arithmetic runs in the sm_100a kernels behind `torch.ops.sa_b200.*`; there is no CPU path.
+Training: a volume / feature map that requires grad makes `corr()`, the constructor and
+`__call__` autograd nodes whose backward runs `sa_lookup_backward` / `sa_pyramid_backward` (and two library
+GEMMs for `corr()`); coords are detached before every lookup in the reference (stereoanywhere.py:268) and must
+not require grad here.
 
 Beyond the strict protocol (used when the caller's wiring allows, reference call sites in
 brackets):
@@ -36,11 +39,79 @@ from . import ops
 _OPS = torch.ops.sa_b200
 
 
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def _no_grad_check(*tensors):
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+    if _needs_grad(*tensors):
         raise NotImplementedError(
-            "CorrBlockB200 is forward-only: inputs must not require grad (wrap the call in torch.no_grad()); "
-            "the reference path's backward is not part of this build")
+            "this stereoanywhere_b200 entry point is forward-only for these inputs: they must not require grad "
+            "(gradients flow to the volume / feature maps only; coords are detached before every lookup in the "
+            "reference, stereoanywhere.py:268)")
+
+
+class _CorrFn(torch.autograd.Function):
+    """`corr()` with a backward: dL = dV . R / sqrt(C), dR = dV^T . L / sqrt(C) (two batched library GEMMs, fp32)."""
+
+    @staticmethod
+    def forward(ctx, f2, f3, prec, post_scale):
+        ctx.save_for_backward(f2, f3)
+        ctx.post_scale = post_scale
+        return _OPS.corr_volume(f2, f3, prec, post_scale)
+
+    @staticmethod
+    def backward(ctx, gvol):
+        f2, f3 = ctx.saved_tensors
+        scale = ctx.post_scale / float(torch.sqrt(torch.tensor(f2.shape[1])))
+        g = gvol.squeeze(3) * scale                                   # [B,H,W2,W3]
+        d2 = torch.einsum("bhwv,bchv->bchw", g, f3) if ctx.needs_input_grad[0] else None
+        d3 = torch.einsum("bhwv,bchw->bchv", g, f2) if ctx.needs_input_grad[1] else None
+        return d2, d3, None, None
+
+
+class _PyramidFn(torch.autograd.Function):
+    """Ties the block to the volume it was built from: returns a 1-element handle; its backward runs after every
+    lookup's backward has accumulated into the block's level-gradient buffers and folds them into dV."""
+
+    @staticmethod
+    def forward(ctx, fullcorr, block):
+        ctx.block = block
+        return fullcorr.new_zeros(1)
+
+    @staticmethod
+    def backward(ctx, _gh):
+        blk = ctx.block
+        b, h, w2, w3 = blk._shape
+        if blk._dlevels is None:  # no lookup took part in the loss
+            return torch.zeros((b, h, w2, 1, w3), dtype=torch.float32, device=_gh.device), None
+        t = blk._truncate
+        d0 = ops._pyramid_backward(blk._dlevels, blk._widths, t[0] if t else None, t[1] if t else None, t[2] if t else 0.0)
+        blk._dlevels = None
+        return d0.view(b, h, w2, 1, w3), None
+
+
+class _LookupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, handle, coords, block):
+        ctx.block = block
+        ctx.save_for_backward(coords)
+        return block._lookup_nograd(coords)
+
+    @staticmethod
+    def backward(ctx, gout):
+        blk = ctx.block
+        (coords,) = ctx.saved_tensors
+        b, h, w2, w3 = blk._shape
+        if blk._dlevels is None:
+            rows = b * h * w2
+            blk._dlevels = [torch.zeros((rows, w3 if i == 0 else ops.level_pitch(w)), dtype=torch.float32, device=gout.device)
+                            for i, w in enumerate(blk._widths)]
+        p0, p1 = blk.pad
+        if p0 or p1:
+            gout = torch.nn.functional.pad(gout, (p0, p1))
+        ops._lookup_backward(gout.float(), coords, blk._dlevels, blk._widths, blk.radius, p0)
+        return torch.zeros(1, dtype=torch.float32, device=gout.device), None, None
 
 
 class CorrBlockB200:
@@ -52,7 +123,8 @@ class CorrBlockB200:
 
     def __init__(self, fullcorr: torch.Tensor, num_levels: int = 4, radius: int = 4, pad: Sequence[int] = (0, 0), *,
                  truncate: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None):
-        _no_grad_check(fullcorr)
+        if truncate is not None:
+            _no_grad_check(truncate[0], truncate[1])  # the mask is detached in the reference (stereoanywhere.py:203)
         if fullcorr.dim() != 5 or fullcorr.shape[3] != 1:
             raise ValueError("fullcorr must be [B, H, W2, 1, W3] (reference corr.py:86)")
         self.num_levels = num_levels
@@ -61,6 +133,11 @@ class CorrBlockB200:
         b, h, w2, _, w3 = fullcorr.shape
         if not fullcorr.is_contiguous():
             fullcorr = fullcorr.contiguous()
+        self._dlevels: Optional[List[torch.Tensor]] = None   # level-gradient accumulators (training only)
+        self._handle: Optional[torch.Tensor] = None
+        grad_src = fullcorr if _needs_grad(fullcorr) else None
+        if grad_src is not None:
+            fullcorr = fullcorr.detach().float()
         self._src = fullcorr            # the tensor handed in (kept alive like the reference does)
         self._truncate = None if truncate is None else (truncate[0], truncate[1], float(truncate[2]))
         self._shape = (b, h, w2, w3)
@@ -74,6 +151,8 @@ class CorrBlockB200:
             self._packed = _OPS.pack_pyramid(rows, t[0] if t else None, t[1] if t else None, t[2] if t else 0.0)
         else:
             self._build_levels()
+        if grad_src is not None:  # training: lookups go through autograd Functions
+            self._handle = _PyramidFn.apply(grad_src.float() if grad_src.dtype != torch.float32 else grad_src, self)
 
     #: "packed" (default; used whenever num_levels=4, radius=4, W3 % 8 == 0, pad=[0,0]) or "levels"
     layout = os.environ.get("SA_B200_LAYOUT", "packed")
@@ -84,10 +163,9 @@ class CorrBlockB200:
         """The mono block of stereoanywhere.py:136 + :257-259 in one pass: the lookup structure of
         `gain * corr(nL, nR)` is written straight from the normal maps; the volume itself is only formed
         if `fullcorr` / `corr_pyramid` are read.  Same values as `cls(cls.mono_corr(nL, nR))`."""
-        _no_grad_check(normals2, normals3)
         b, c, h, w2 = normals2.shape
         w3 = normals3.shape[3]
-        if not (cls.layout == "packed" and ops.packable(num_levels, radius, w3, [0, 0])):
+        if _needs_grad(normals2, normals3) or not (cls.layout == "packed" and ops.packable(num_levels, radius, w3, [0, 0])):
             return cls(cls.mono_corr(normals2, normals3, gain), num_levels=num_levels, radius=radius)
         self = cls.__new__(cls)
         self.num_levels, self.radius, self.pad = num_levels, radius, [0, 0]
@@ -97,6 +175,7 @@ class CorrBlockB200:
         self._shape = (b, h, w2, w3)
         self._widths = ops.level_widths(w3, num_levels)
         self._levels = None
+        self._dlevels, self._handle = None, None
         self._packed = _OPS.pack_pyramid_normals(self._normals[0], self._normals[1], float(gain))
         return self
 
@@ -109,11 +188,10 @@ class CorrBlockB200:
         `cls(cls.corr(fmap2, fmap3), truncate=truncate)` in tf32 precision; the volume is only formed if
         `fullcorr` / `corr_pyramid` are read.  Falls back to that two-step form for shapes the fused kernel
         does not cover, or when `precision == "fp32"`."""
-        _no_grad_check(fmap2, fmap3)
         b, c, h, w2 = fmap2.shape
         w3 = fmap3.shape[3]
-        if not (cls.layout == "packed" and cls.precision == "tf32" and ops.packable(num_levels, radius, w3, [0, 0])
-                and ops.corr_packable(c, w2, w3)):
+        if _needs_grad(fmap2, fmap3) or not (cls.layout == "packed" and cls.precision == "tf32"
+                                             and ops.packable(num_levels, radius, w3, [0, 0]) and ops.corr_packable(c, w2, w3)):
             return cls(cls.corr(fmap2, fmap3), num_levels=num_levels, radius=radius, truncate=truncate)
         self = cls.__new__(cls)
         self.num_levels, self.radius, self.pad = num_levels, radius, [0, 0]
@@ -123,6 +201,7 @@ class CorrBlockB200:
         self._shape = (b, h, w2, w3)
         self._widths = ops.level_widths(w3, num_levels)
         self._levels = None
+        self._dlevels, self._handle = None, None
         t = self._truncate
         self._packed = _OPS.corr_pack(self._features[0], self._features[1], t[0] if t else None, t[1] if t else None,
                                       t[2] if t else 0.0)
@@ -162,15 +241,20 @@ class CorrBlockB200:
         With the packed layout they are built on first access.)"""
         return [lv[:, :w].unsqueeze(1).unsqueeze(1) for lv, w in zip(self._build_levels(), self._widths)]
 
+    def _lookup_nograd(self, coords: torch.Tensor) -> torch.Tensor:
+        if self._packed is not None:
+            return _OPS.lookup_packed(self._packed, self._shape[3], coords)
+        return _OPS.lookup(self._levels, self._widths, coords, self.radius, self.pad[0], self.pad[1])
+
     def __call__(self, coords: torch.Tensor) -> torch.Tensor:
         _no_grad_check(coords)
         dt = coords.dtype
         if dt != torch.float32:
             coords = coords.float()
-        if self._packed is not None:
-            out = _OPS.lookup_packed(self._packed, self._shape[3], coords)
+        if self._handle is not None and torch.is_grad_enabled():
+            out = _LookupFn.apply(self._handle, coords, self)
         else:
-            out = _OPS.lookup(self._levels, self._widths, coords, self.radius, self.pad[0], self.pad[1])
+            out = self._lookup_nograd(coords)
         return out if dt == torch.float32 else out.to(dt)
 
     # ---- protocol: static corr --------------------------------------------------------------
@@ -180,27 +264,33 @@ class CorrBlockB200:
 
         C % 8 == 0 and 4-aligned widths take the tensor-core kernel in `CorrBlockB200.precision`;
         anything else (the C=3 normals volume in particular) takes the fp32 SIMT kernel."""
-        _no_grad_check(fmap2, fmap3)
         dt = fmap2.dtype
         f2, f3 = fmap2.float(), fmap3.float()
         prec = CorrBlockB200.precision
         c, w2, w3 = f2.shape[1], f2.shape[3], f3.shape[3]
         if prec != "fp32" and not (c % 8 == 0 and c >= 32 and w2 % 4 == 0 and w3 % 4 == 0 and w3 <= 1024):
             prec = "fp32"
-        vol = _OPS.corr_volume(f2, f3, prec, 1.0)
+        if _needs_grad(f2, f3):
+            vol = _CorrFn.apply(f2, f3, prec, 1.0)
+        else:
+            vol = _OPS.corr_volume(f2, f3, prec, 1.0)
         return vol if dt == torch.float32 else vol.to(dt)
 
     # ---- beyond the protocol ------------------------------------------------------------------
     @staticmethod
     def mono_corr(normals2: torch.Tensor, normals3: torch.Tensor, gain: float = 1.73) -> torch.Tensor:
         """`1.73 * corr(nL, nR)` in one pass (stereoanywhere.py:136)."""
-        _no_grad_check(normals2, normals3)
-        return _OPS.corr_volume(normals2.float(), normals3.float(), "fp32", float(gain))
+        n2, n3 = normals2.float(), normals3.float()
+        if _needs_grad(n2, n3):
+            return _CorrFn.apply(n2, n3, "fp32", float(gain))
+        return _OPS.corr_volume(n2, n3, "fp32", float(gain))
 
     @staticmethod
     def lookup_pair(block_a: "CorrBlockB200", block_b: "CorrBlockB200", coords: torch.Tensor):
         """`(block_a(coords), block_b(coords))` with one launch (stereoanywhere.py:270-271)."""
         _no_grad_check(coords)
+        if torch.is_grad_enabled() and (block_a._handle is not None or block_b._handle is not None):
+            return block_a(coords), block_b(coords)  # training: each lookup is its own autograd node
         if (block_a.radius != block_b.radius or block_a._widths != block_b._widths
                 or block_a.pad != [0, 0] or block_b.pad != [0, 0]
                 or (block_a._packed is None) != (block_b._packed is None)):

@@ -313,6 +313,43 @@ def _volume_entropy_conf(vol: torch.Tensor):
     return _volume_reduce(vol, "entropy_conf")
 
 
+def _lookup_backward(grad_out: torch.Tensor, coords: torch.Tensor, dlevels: List[torch.Tensor], widths: List[int],
+                     radius: int, pad0: int) -> None:
+    """Accumulate the adjoint of one lookup into the level-gradient buffers `dlevels` (csrc/backward.cu).
+    grad_out is [B, L*(2r+1), H, W - pad]; pad != 0 is handled by the caller (it zero-pads grad_out)."""
+    coords, b, h, w = _coords_view(coords)
+    _cuda_f32(grad_out, "grad_out")
+    n, ptrs, wid, pit = _marshal(dlevels, widths)
+    _req(grad_out.shape == (b, n * (2 * radius + 1), h, w), "grad_out does not match coords / levels")
+    _req(dlevels[0].shape[0] == b * h * w, "level-gradient buffers do not match coords")
+    grad_out = grad_out.contiguous()
+    lib = _lib.load()
+    with _on(coords.device):
+        rc = lib.sa_lookup_backward(grad_out.data_ptr(), coords.data_ptr(), coords.stride(0), ptrs, wid, pit, n, radius,
+                                    b, h, w, pad0, _stream_ptr(coords))
+    _lib.check(rc, "sa_lookup_backward")
+
+
+def _pyramid_backward(dlevels: List[torch.Tensor], widths: List[int], trunc_disp: Optional[torch.Tensor],
+                      trunc_conf: Optional[torch.Tensor], trunc_gain: float) -> torch.Tensor:
+    """Fold the level gradients into level 0 in place and return it ([rows, W], the gradient w.r.t. the volume)."""
+    n, ptrs, wid, pit = _marshal(dlevels, widths)
+    rows = dlevels[0].shape[0]
+    lib = _lib.load()
+    td = tc = None
+    w2 = 0
+    if trunc_disp is not None:
+        trunc_disp, trunc_conf = trunc_disp.contiguous(), trunc_conf.contiguous()
+        _cuda_f32(trunc_disp, "trunc_disp")
+        _cuda_f32(trunc_conf, "trunc_conf")
+        td, tc, w2 = trunc_disp.data_ptr(), trunc_conf.data_ptr(), trunc_disp.shape[-1]
+    with _on(dlevels[0].device):
+        rc = lib.sa_pyramid_backward(dlevels[0].data_ptr(), ptrs, wid, pit, n, rows, td, tc, float(trunc_gain), w2,
+                                     _stream_ptr(dlevels[0]))
+    _lib.check(rc, "sa_pyramid_backward")
+    return dlevels[0]
+
+
 def _lookup_packed(packed_a: torch.Tensor, packed_b: Optional[torch.Tensor], w3: int, coords: torch.Tensor):
     coords, b, h, w = _coords_view(coords)
     _cuda_f32(packed_a, "packed pyramid")

@@ -54,3 +54,8 @@ def golden_tiles():
 @pytest.fixture(scope="session")
 def golden_reductions():
     return dict(np.load(os.path.join(GOLDEN, "reductions.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_grads():
+    return dict(np.load(os.path.join(GOLDEN, "grads.npz")))

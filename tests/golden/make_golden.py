@@ -258,8 +258,46 @@ def reductions():
     print("reductions.npz", sum(np.asarray(v).nbytes for v in out.values()) / 1e6, "MB raw")
 
 
+def grads():
+    """gradients of the reference block (autograd through einsum / avg_pool2d / grid_sample and the
+    detached truncation product, as in train.py:277,383) on seeded inputs."""
+    CorrBlock1D, U = ref_shim.import_reference_corr()
+    g = torch.Generator().manual_seed(2468)
+    out = {}
+    for tag, (b, h, w) in [("w24", (1, 3, 24)), ("w39", (1, 2, 39)), ("w40", (2, 2, 40))]:
+        v = torch.randn(b, h, w, 1, w, generator=g).requires_grad_(True)
+        x = torch.arange(w, dtype=torch.float32).view(1, 1, 1, w).repeat(b, 1, h, 1)
+        coords = [torch.cat([x - torch.rand(b, 1, h, w, generator=g) * (w / 3) + k, torch.zeros(b, 1, h, w)], 1) for k in range(3)]
+        wts = [torch.randn(b, 36, h, w, generator=g) for _ in range(3)]
+        blk = CorrBlock1D(v, num_levels=4, radius=4)
+        loss = sum((blk(c) * wt).sum() for c, wt in zip(coords, wts))
+        (dv,) = torch.autograd.grad(loss, v)
+        out.update({f"{tag}_vol": _np(v.detach()), f"{tag}_dvol": _np(dv)})
+        for k in range(3):
+            out[f"{tag}_coords{k}"] = _np(coords[k])
+            out[f"{tag}_w{k}"] = _np(wts[k])
+        # through the truncation product (mask detached, stereoanywhere.py:203, 253-255)
+        disp = torch.rand(b, 1, h, w, generator=g) * (w / 4)
+        conf = torch.rand(b, 1, h, w, generator=g)
+        tmask = U.truncate_corr_volume_v2(disp, conf, conf_th=None, attenuation_gain=0.9).detach()
+        v2 = v.detach().clone().requires_grad_(True)
+        blk2 = CorrBlock1D((tmask * v2.squeeze(3).unsqueeze(1)).squeeze(1).unsqueeze(3), num_levels=4, radius=4)
+        loss2 = sum((blk2(c) * wt).sum() for c, wt in zip(coords, wts))
+        (dv2,) = torch.autograd.grad(loss2, v2)
+        out.update({f"{tag}_tdisp": _np(disp), f"{tag}_tconf": _np(conf), f"{tag}_dvol_trunc": _np(dv2)})
+    # corr(): gradients to the feature maps
+    fl = torch.randn(2, 32, 3, 24, generator=g).requires_grad_(True)
+    fr = torch.randn(2, 32, 3, 24, generator=g).requires_grad_(True)
+    wv = torch.randn(2, 3, 24, 1, 24, generator=g)
+    vol = CorrBlock1D.corr(fl, fr)
+    dfl, dfr = torch.autograd.grad((vol * wv).sum(), (fl, fr))
+    out.update(c_fl=_np(fl.detach()), c_fr=_np(fr.detach()), c_w=_np(wv), c_dfl=_np(dfl), c_dfr=_np(dfr))
+    np.savez_compressed(os.path.join(HERE, "grads.npz"), **out)
+    print("grads.npz", sum(np.asarray(v).nbytes for v in out.values()) / 1e6, "MB raw")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["path_small", "model_slice", "tiles", "reductions"]
-    for name in which:
-        {"path_small": path_small, "model_slice": model_slice, "tiles": tiles, "reductions": reductions}[name]()
+    table = {"path_small": path_small, "model_slice": model_slice, "tiles": tiles, "reductions": reductions, "grads": grads}
+    for name in sys.argv[1:] or list(table):
+        table[name]()

@@ -492,3 +492,94 @@ def test_pack_normals_matches_two_step(sa, shape):
     x = torch.arange(w2, dtype=torch.float32).view(1, 1, 1, w2).expand(b, 1, h, w2)
     coords = torch.cat([x - torch.rand(b, 1, h, w2, generator=gen) * (w3 / 4), torch.zeros(b, 1, h, w2)], 1).to(DEV)
     assert torch.equal(fused(coords), two(coords))
+
+
+# ------------------------------------------------------------------------------------------ 8f-4 backward
+@pytest.mark.parametrize("tag", ["w24", "w39", "w40"])
+@pytest.mark.parametrize("layout", ["packed", "levels"])
+def test_golden_gradients(sa, golden_grads, tag, layout):
+    """Gradient w.r.t. the volume of three lookups (and through the truncation product) vs the gradients the
+    reference's own autograd produced (fixtures)."""
+    g = golden_grads
+    B = sa.CorrBlockB200
+    old = B.layout
+    B.layout = layout
+    try:
+        coords = [G(g[f"{tag}_coords{k}"]) for k in range(3)]
+        wts = [G(g[f"{tag}_w{k}"]) for k in range(3)]
+        v = G(g[f"{tag}_vol"]).requires_grad_(True)
+        blk = B(v, num_levels=4, radius=4)
+        assert (blk._packed is not None) == (layout == "packed" and tag != "w39")
+        loss = sum((blk(c) * w).sum() for c, w in zip(coords, wts))
+        (dv,) = torch.autograd.grad(loss, v)
+        assert dv.shape == v.shape
+        assert maxabs(dv, g[f"{tag}_dvol"]) < 2e-5
+        # fused truncation: gradient w.r.t. V of the block built from T * V (T detached)
+        v2 = G(g[f"{tag}_vol"]).requires_grad_(True)
+        blk2 = B(v2, num_levels=4, radius=4, truncate=(G(g[f"{tag}_tdisp"]), G(g[f"{tag}_tconf"]), 0.9))
+        loss2 = sum((blk2(c) * w).sum() for c, w in zip(coords, wts))
+        (dv2,) = torch.autograd.grad(loss2, v2)
+        assert maxabs(dv2, g[f"{tag}_dvol_trunc"]) < 2e-5
+        # strict protocol: the caller forms the product itself, autograd handles the multiply
+        v3 = G(g[f"{tag}_vol"]).requires_grad_(True)
+        t = sa.truncation_mask(G(g[f"{tag}_tdisp"]), G(g[f"{tag}_tconf"]), 0.9)
+        blk3 = B((t * v3.squeeze(3).unsqueeze(1)).squeeze(1).unsqueeze(3), num_levels=4, radius=4)
+        (dv3,) = torch.autograd.grad(sum((blk3(c) * w).sum() for c, w in zip(coords, wts)), v3)
+        assert maxabs(dv3, g[f"{tag}_dvol_trunc"]) < 2e-5
+        # forward values under grad mode are those of the no-grad path
+        with torch.no_grad():
+            ref = B(v.detach())(coords[0])
+        assert torch.equal(blk(coords[0]).detach(), ref)
+    finally:
+        B.layout = old
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tf32"])
+def test_golden_corr_gradients(sa, golden_grads, prec):
+    g = golden_grads
+    B = sa.CorrBlockB200
+    old = B.precision
+    B.precision = prec
+    try:
+        fl, fr = G(g["c_fl"]).requires_grad_(True), G(g["c_fr"]).requires_grad_(True)
+        vol = B.corr(fl, fr)
+        dfl, dfr = torch.autograd.grad((vol * G(g["c_w"])).sum(), (fl, fr))
+        assert normwise(dfl, g["c_dfl"]) < 2e-6 and normwise(dfr, g["c_dfr"]) < 2e-6  # backward is fp32 GEMM
+    finally:
+        B.precision = old
+
+
+def test_training_step_gradients_vs_oracle(sa):
+    """A miniature training step - corr(), truncation, both blocks, four GRU-like iterations with detached
+    coords - differentiated through the CUDA path and through the oracle's ATen op sequence on the CPU."""
+    gen = torch.Generator().manual_seed(99)
+    b, c, h, w = 2, 64, 4, 72
+    fl, fr = torch.randn(b, c, h, w, generator=gen), torch.randn(b, c, h, w, generator=gen)
+    mono = torch.randn(b, h, w, 1, w, generator=gen)   # stands in for the hourglass output (stereoanywhere.py:210)
+    tdisp, tconf = torch.rand(b, 1, h, w, generator=gen) * (w / 4), torch.rand(b, 1, h, w, generator=gen)
+    x = torch.arange(w, dtype=torch.float32).view(1, 1, 1, w).repeat(b, 1, h, 1)
+    coords = [torch.cat([x - torch.rand(b, 1, h, w, generator=gen) * (w / 4), torch.zeros(b, 1, h, w)], 1) for _ in range(4)]
+    ws = [torch.randn(b, 36, h, w, generator=gen) for _ in range(4)]
+    wm = [torch.randn(b, 36, h, w, generator=gen) for _ in range(4)]
+
+    def run(block_cls, corr_fn, tmask_fn, dev):
+        f2, f3 = fl.to(dev).requires_grad_(True), fr.to(dev).requires_grad_(True)
+        mv = mono.to(dev).requires_grad_(True)
+        vol = corr_fn(f2, f3)
+        t = tmask_fn(tdisp.to(dev), tconf.to(dev))
+        sfn = block_cls((t * vol.squeeze(3).unsqueeze(1)).squeeze(1).unsqueeze(3), num_levels=4, radius=4)
+        mfn = block_cls(mv, num_levels=4, radius=4)
+        loss = 0
+        for k in range(4):
+            cd = coords[k].to(dev).detach()
+            loss = loss + (sfn(cd) * ws[k].to(dev)).sum() + (mfn(cd) * wm[k].to(dev)).sum()
+        return torch.autograd.grad(loss, (f2, f3, mv))
+
+    sa.CorrBlockB200.precision = "fp32"
+    try:
+        got = run(sa.CorrBlockB200, sa.CorrBlockB200.corr, lambda d, cf: sa.truncation_mask(d, cf, 0.9), DEV)
+    finally:
+        sa.CorrBlockB200.precision = "tf32"
+    want = run(O.OracleCorrBlock, O.aten_corr_volume, lambda d, cf: O.aten_truncation_mask(d, cf, 0.9), "cpu")
+    for a_, b_ in zip(got, want):
+        assert normwise(a_, b_) < 1e-5

@@ -73,9 +73,14 @@ def test_level_geometry():
     assert [ops.level_pitch(w) for w in (312, 156, 78, 39)] == [312, 156, 80, 40]
 
 
-def test_requires_grad_is_rejected():
-    import stereoanywhere_b200 as sa
+def test_grad_policy():
+    """Gradients flow to volumes / feature maps; coords and the truncation maps must be detached."""
+    from stereoanywhere_b200 import corr as C
 
-    v = torch.zeros(1, 2, 8, 1, 8, requires_grad=True)
+    t = torch.zeros(1, requires_grad=True)
+    assert C._needs_grad(t) and not C._needs_grad(t.detach())
+    with torch.no_grad():
+        assert not C._needs_grad(t)
     with pytest.raises(NotImplementedError):
-        sa.CorrBlockB200(v)
+        C._no_grad_check(None, t)
+    C._no_grad_check(None, t.detach())

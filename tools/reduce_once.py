@@ -5,7 +5,6 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 import stereoanywhere_b200 as sa
-from oracle import corr_oracle as O   # only as the timed ATen comparison / checker
 name = sys.argv[1] if len(sys.argv) > 1 else bench.DEFAULT_WORKLOAD
 b, c, h, w = bench.WORKLOADS[name]
 dev = torch.device("cuda:0")

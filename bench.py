@@ -45,6 +45,12 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "c2_kitti_375x1242_b8"
 ITERS, LEVELS, RADIUS = 32, 4, 4
 METRIC = "stereo pairs/sec @375x1242, 32 iters (cost-volume path: corr + pyramid + lookup)"
+METRIC_SIZES = {"c1_384x512_b1": "384x512", "c2_kitti_375x1242_b8": "375x1242", "c3_sceneflow_540x960_b8": "540x960",
+                "c4_middlebury_tile_1120x672_b1": "1120x672 (one Middlebury tile)", "c5_sweep_c256_w768_b1": "384x3072 (W/4 = 768)"}
+
+
+def metric_for(workload):
+    return METRIC.replace("375x1242", METRIC_SIZES.get(workload, "375x1242"))
 UNIT = "pairs/s"
 
 
@@ -369,7 +375,7 @@ def run_gpu(args):
                 "path_algorithmic_gbs": round(path_bytes(b, c, h, w) / (ms_step * 1e-3) / 1e9, 1)}
         cpu = None if args.no_cpu_baseline else cpu_baseline(args.workload, sample_pairs=args.cpu_pairs, reps=3)
         result = {
-            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_for(args.workload), "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": f"{args.precision} corr (fp32 accumulate), f32 pyramid/lookup",
             "data": "synthetic (seeded N(0,1) features, unit normals, U(0,W/4) disparities)",
@@ -594,7 +600,7 @@ def run_reference(args):
     sample = (f"each step = {pairs} of {b} pairs of {args.workload}, all {ITERS} iterations, oracle port of the "
               f"reference op sequence (einsum, avg_pool2d, grid_sample) on CPU")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_for(args.workload), "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(t / args.steps * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "pairs_per_step": pairs, "iters": ITERS, "levels": LEVELS, "radius": RADIUS},

@@ -54,6 +54,15 @@ def metric_for(workload):
 UNIT = "pairs/s"
 
 
+def tensor_peak_tf32():
+    """Dense TF32 tensor peak in TFLOP/s: half the measured bf16 cuBLAS burst figure (MEASURED_PEAKS.json), else
+    half the profiling guide's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return round(float(json.load(open(p))["bf16_tflops"]) / 2.0, 1)
+    return 795.0
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -159,6 +168,16 @@ class GpuPath:
         self.ev = None  # (start, end) events around the lookup loop of the current step
         self.launches = 0
 
+    def build_stereo(self):
+        B, d = self.sa.CorrBlockB200, self.d
+        self.launches += 1
+        return B.from_features(d["fl"], d["fr"], radius=RADIUS, num_levels=LEVELS, truncate=(d["tdisp"], d["tconf"], 0.9))
+
+    def build_mono(self):
+        B, d = self.sa.CorrBlockB200, self.d
+        self.launches += 1
+        return B.from_normals(d["nl"], d["nr"], radius=RADIUS, num_levels=LEVELS)
+
     def build(self):
         sa, d = self.sa, self.d
         B = sa.CorrBlockB200
@@ -263,29 +282,43 @@ def run_gpu(args):
 
     for _ in range(max(args.warmup, 3)):
         collective(path.step())
-    g_build = g_look = None
+    g_build = g_look = g_mono = None
     if args.graph:
-        # The step is ~35 launches of 10-400 us: replay it from two CUDA graphs (volumes + packing, then
-        # the 32 lookups) so that the events around the second graph time the lookup kernels alone.
+        # The step is ~35 launches of 10-400 us: replay it from CUDA graphs (stereo volume + packing; mono packing;
+        # the 32 lookups) so that the events between the graphs time each kernel family alone.
         torch.cuda.synchronize()
         seq = path.coords_seq()
         g_build, g_look = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_build):
-            fs, fm = path.build()
+        if args.variant == "fused":
+            g_mono = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_build):
+                fs = path.build_stereo()
+            with torch.cuda.graph(g_mono, pool=g_build.pool()):
+                fm = path.build_mono()
+        else:
+            with torch.cuda.graph(g_build):
+                fs, fm = path.build()
         with torch.cuda.graph(g_look, pool=g_build.pool()):
             g_out = path.lookups(fs, fm, seq)
         for _ in range(2):
             g_build.replay()
+            if g_mono is not None:
+                g_mono.replay()
             g_look.replay()
     drain()
     barrier()
     path.launches = 0
     lk_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    bd_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(args.steps):
         if g_build is not None:
+            bd_events[k][0].record()
             g_build.replay()
+            bd_events[k][1].record()
+            if g_mono is not None:
+                g_mono.replay()
             lk_events[k][0].record()
             g_look.replay()
             lk_events[k][1].record()
@@ -299,6 +332,11 @@ def run_gpu(args):
     ms_total = e0.elapsed_time(e1)
     launches = path.launches if g_build is None else args.steps * (34 if args.variant == "fused" else 69)
     lk_ms = sum(a.elapsed_time(bb) for a, bb in lk_events) / args.steps
+    breakdown = None
+    if g_mono is not None:  # fused variant under graphs: one kernel per graph for the two builders
+        st_ms = sum(a.elapsed_time(bb) for a, bb in bd_events) / args.steps
+        mo_ms = sum(bd_events[k][1].elapsed_time(lk_events[k][0]) for k in range(args.steps)) / args.steps
+        breakdown = (st_ms, mo_ms)
     n_lk_launch = ITERS if args.variant == "fused" else 2 * ITERS
     lk_launch_ms = lk_ms / n_lk_launch
 
@@ -373,6 +411,23 @@ def run_gpu(args):
                 "traffic": TRAFFIC_BYTES.get((args.workload, args.variant)), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg, "launch_us": round(lk_launch_ms * 1e3, 2),
                 "path_algorithmic_gbs": round(path_bytes(b, c, h, w) / (ms_step * 1e-3) / 1e9, 1)}
+        kernels = None
+        if breakdown is not None:
+            st_us, mo_us = breakdown[0] * 1e3, breakdown[1] * 1e3
+            packed = p * (w // 8 + 9) * 128
+            tf32_peak = tensor_peak_tf32()
+            tflops = 2.0 * p * w * c / (st_us * 1e-6) / 1e12
+            kernels = {
+                "corr_pack_tf32": {"us": round(st_us, 1), "hbm_gbs": round((2 * b * c * h * w * 4 + packed) / st_us / 1e3, 1),
+                                   "hbm_frac": round((2 * b * c * h * w * 4 + packed) / st_us / 1e3 / peak, 4),
+                                   "tflops": round(tflops, 1), "tensor_peak_tf32": tf32_peak,
+                                   "tensor_frac": round(tflops / tf32_peak, 4),
+                                   "note": "HBM-bound by the packed write; the tensor pipe is reported, not targeted"},
+                "pack_normals": {"us": round(mo_us, 1), "hbm_gbs": round(packed / mo_us / 1e3, 1), "hbm_frac": round(packed / mo_us / 1e3 / peak, 4)},
+                "lookup_packed2": {"us": round(lk_launch_ms * 1e3, 2), "launches": n_lk_launch,
+                                   "hbm_gbs_real_bytes": round(544 * p / (lk_launch_ms * 1e-3) / 1e9, 1),
+                                   "hbm_frac_real_bytes": round(544 * p / (lk_launch_ms * 1e-3) / 1e9 / peak, 4)},
+            }
         cpu = None if args.no_cpu_baseline else cpu_baseline(args.workload, sample_pairs=args.cpu_pairs, reps=3)
         result = {
             "metric": metric_for(args.workload), "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -388,6 +443,7 @@ def run_gpu(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,
+            "kernels": kernels,
             "cpu_baseline": cpu,
         }
         print(json.dumps(result), flush=True)

@@ -253,18 +253,31 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
   }
   __syncthreads();
 
-  // ---- stage one line per (pixel, volume): 8 lanes x 16 B, chunk c of pixel p lands at chunk c ^ (p & 7)
+  // ---- stage one line per (pixel, volume): 8 lanes x 16 B, chunk c of pixel p lands at chunk c ^ (p & 7).
+  // Thread tid copies chunk ch = tid & 7 of the units (tid >> 3) + n * THREADS/8, n < 8: the volume of a unit is
+  // a compile-time function of n and its pixel one of 8/NV values, so the 64-bit line addresses are formed
+  // 8/NV times per thread and shared by the volumes.
+  {
+    constexpr int UPS = THREADS / 8;   // units per step
+    constexpr int SPV = 8 / NV;        // steps per volume
+    const int ch = tid & 7, u0 = tid >> 3;
+    long long goff[SPV];               // float offset of this thread's chunk inside a packed array, or -1
 #pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    const int idx = tid + n * THREADS;
-    const int unit = idx >> 3, ch = idx & 7;
-    const int v = unit / TILE, p = unit % TILE;
-    float* dst = buf + unit * 32 + ((ch ^ (p & 7)) << 2);
-    const int blk = s_blk[p];
-    if (blk >= 0)
-      cp_async16(dst, (v ? a.packed[1] : a.packed[0]) + ((row0 + p) * a.nblk + blk) * 32 + ch * 4);
-    else
-      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = 0; m < SPV; ++m) {
+      const int pm = u0 + m * UPS;
+      const int blk = s_blk[pm];
+      goff[m] = blk >= 0 ? ((row0 + pm) * (long long)a.nblk + blk) * 32 + ch * 4 : -1;
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int v = n / SPV, m = n % SPV;  // compile-time
+      const int pm = u0 + m * UPS;
+      float* dst = buf + (v * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2);
+      if (goff[m] >= 0)
+        cp_async16(dst, (v ? a.packed[1] : a.packed[0]) + goff[m]);
+      else
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -346,14 +359,21 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
 
   // ---- [channel][pixel] tile -> NCHW
   if ((a.HW & 3) == 0) {
+    // thread tid always stores pixels t .. t+3 of the channels c0 + 4 NV k, k < NC/4: one pointer per volume,
+    // advanced by a constant stride - no division, no 64-bit multiply in the loop
     constexpr int T4 = TILE / 4;
-    for (int idx = tid; idx < NV * NC * T4; idx += THREADS) {
-      const int c = idx / T4;
-      const int t = (idx % T4) * 4;
-      if (t < npx) {
+    static_assert(THREADS == 4 * NV * T4 && NC % 4 == 0, "store mapping");
+    const int c0 = tid / T4, t = (tid % T4) * 4;
+    if (t < npx) {
+      const long long pix = (long long)b * NC * a.HW + hw0 + t;
+      const long long cstride = (long long)a.HW;
+#pragma unroll
+      for (int k = 0; k < NC / 4; ++k) {
+        const int c = c0 + 4 * NV * k;          // 0 .. NV*NC-1
+        const int vv = (NV == 2 && c >= NC) ? 1 : 0;
+        const int cc = c - vv * NC;
         const float4 val = *reinterpret_cast<const float4*>(buf + c * SP + t);
-        const int vv = c / NC, cc = c - vv * NC;
-        st_stream_v4((vv ? a.out[1] : a.out[0]) + ((long long)b * NC + cc) * a.HW + hw0 + t, val);
+        st_stream_v4((vv ? a.out[1] : a.out[0]) + pix + cc * cstride, val);
       }
     }
   } else {

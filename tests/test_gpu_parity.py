@@ -363,6 +363,17 @@ def test_full_size_properties(sa, cfg):
     xin = torch.rand(b, 1, h, w, device=DEV, generator=gen) * (w - 80) + 40
     oc = ones(torch.cat([xin, torch.zeros_like(xin)], 1))
     assert float((oc[:, :9] - 1.0).abs().max()) < 1e-6
+    # (6) the fused constructors at full size: same packed arrays as the two-step forms, bit for bit
+    del blk2, ones, o2, oc
+    tdisp = torch.rand(b, 1, h, w, device=DEV, generator=gen) * (w / 4)
+    tconf = torch.rand(b, 1, h, w, device=DEV, generator=gen)
+    two = sa.CorrBlockB200(vol, truncate=(tdisp, tconf, 0.9))
+    one = sa.CorrBlockB200.from_features(fl, fr, truncate=(tdisp, tconf, 0.9))
+    assert torch.equal(one._packed, two._packed)
+    del one, two
+    nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w, device=DEV, generator=gen), dim=1)
+    nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w, device=DEV, generator=gen), dim=1)
+    assert torch.equal(sa.CorrBlockB200.from_normals(nl, nr)._packed, sa.CorrBlockB200(sa.CorrBlockB200.mono_corr(nl, nr))._packed)
 
 
 def test_lookup_fused_with_convc1(sa):

@@ -98,6 +98,8 @@ extern "C" int sa_corr_fp32(const float* fmap_l, const float* fmap_r, float* vol
   SA_REQUIRE(B > 0 && C > 0 && H > 0 && W2 > 0 && W3 > 0, SA_E_INVALID, "sa_corr_fp32: sizes must be positive");
   SA_REQUIRE(divisor != 0.f, SA_E_INVALID, "sa_corr_fp32: divisor == 0");
   SA_REQUIRE(aligned16(vol), SA_E_ALIGN, "sa_corr_fp32: vol must be 16-byte aligned");
+  if (C == 3 && (W3 & 3) == 0 && aligned16(fmap_r))  // the mono volume: a streaming write, one warp per volume row
+    return launch_mono_volume_rows(fmap_l, fmap_r, vol, B, H, W2, W3, divisor, post_scale, (cudaStream_t)stream);
   const int tiles_m = (W2 + kTile - 1) / kTile, tiles_n = (W3 + kTile - 1) / kTile;
   const long long blocks = (long long)B * H * tiles_m * tiles_n;
   SA_REQUIRE(blocks < (1ll << 31), SA_E_UNSUPPORTED, "sa_corr_fp32: too many tiles");

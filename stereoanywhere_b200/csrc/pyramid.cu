@@ -194,6 +194,8 @@ extern "C" int sa_truncate(const float* vol, const float* disp, const float* con
   using namespace sa;
   SA_REQUIRE(disp && conf && out && rows > 0 && W2 > 0 && W3 > 0 && rows % W2 == 0, SA_E_INVALID,
              "sa_truncate: bad arguments");
+  if ((W3 & 3) == 0 && aligned16(out) && (!vol || aligned16(vol)))
+    return launch_truncate_rows(vol, disp, conf, (float)gain, (float)(1.0 - gain), out, rows, W2, W3, (cudaStream_t)stream);
   const long long n = rows * (long long)W3;
   const long long want = (n + 255) / 256;
   const int grid = (int)(want < (long long)num_sms() * 32 ? want : (long long)num_sms() * 32);

@@ -113,6 +113,9 @@ extern "C" int sa_masked_volume(const float* vol, const float* normals_l, const 
   SA_REQUIRE(n_bins >= 1 && n_bins <= SA_MAX_BINS, SA_E_INVALID, "sa_masked_volume: 1 <= n_bins <= %d", SA_MAX_BINS);
   SA_REQUIRE(B > 0 && H > 0 && W2 > 0 && W3 > 0, SA_E_INVALID, "sa_masked_volume: sizes must be positive");
   SA_REQUIRE((W3 & 3) != 0 || aligned16(out), SA_E_ALIGN, "sa_masked_volume: out must be 16-byte aligned");
+  if ((W3 & 3) == 0 && aligned16(out) && aligned16(mde_r) && (vol ? aligned16(vol) : aligned16(normals_r)))
+    return launch_masked_volume_rows(vol, normals_l, normals_r, divisor, post_scale, mde_l, mde_r, h_edges, n_bins, out, B, H,
+                                     W2, W3, (cudaStream_t)stream);
   BinEdges ed;
   for (int i = 0; i <= n_bins; ++i) ed.e[i] = h_edges[i];
   for (int i = n_bins + 1; i <= SA_MAX_BINS; ++i) ed.e[i] = 0.f;
@@ -137,6 +140,9 @@ extern "C" int sa_corrupt(const float* vol, const float* bin_mask, int mode, int
   SA_REQUIRE(mode >= 0 && mode <= 2, SA_E_INVALID, "sa_corrupt: mode must be 0 (roll), 1 (noise) or 2 (gauss)");
   SA_REQUIRE(mode != 1 || noise, SA_E_INVALID, "sa_corrupt: noise mode needs a noise map");
   SA_REQUIRE(B > 0 && H > 0 && W2 > 0 && W3 > 0, SA_E_INVALID, "sa_corrupt: sizes must be positive");
+  if ((W3 & 3) == 0 && aligned16(vol) && aligned16(out))
+    return launch_corrupt_rows(vol, bin_mask, mode, shift, noise, gauss_k, out, (long long)B * H * W2, W2, W3,
+                               (cudaStream_t)stream);
   const long long n = (long long)B * H * W2 * W3;
   const long long want = (n + 255) / 256;
   const int grid = (int)(want < (long long)num_sms() * 32 ? want : (long long)num_sms() * 32);

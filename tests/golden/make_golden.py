@@ -296,8 +296,33 @@ def grads():
     print("grads.npz", sum(np.asarray(v).nbytes for v in out.values()) / 1e6, "MB raw")
 
 
+def producers():
+    """generate_masks, estimate_normals (kornia stub), weighted_lsq of the reference."""
+    _, U = ref_shim.import_reference_corr()
+    g = torch.Generator().manual_seed(1357)
+    out = {}
+    mde = torch.rand(2, 1, 12, 20, generator=g)
+    mde[0, 0, 0, 0], mde[0, 0, 0, 1], mde[1, 0, 3, 3] = 1.0, 0.0, 0.5
+    out["gm_mde"] = _np(mde)
+    for n in (4, 8, 16):
+        out[f"gm_masks{n}"] = _np(U.generate_masks(mde, N=n))
+    depth = torch.rand(2, 1, 12, 20, generator=g)
+    out["en_depth"] = _np(depth)
+    out["en_normals"] = _np(U.estimate_normals(depth, normal_gain=20 / 10))
+    b, h, w = 3, 24, 40
+    mono = torch.rand(b, 2, h, w, generator=g)
+    disp = (mono * torch.tensor([3.0, 5.0, 0.5]).view(b, 1, 1, 1) + torch.tensor([1.0, -0.5, 2.0]).view(b, 1, 1, 1)
+            + 0.05 * torch.randn(b, 2, h, w, generator=g))
+    conf = torch.rand(b, 2, h, w, generator=g)
+    sc, sh = U.weighted_lsq(mono, disp, conf)
+    out.update(wl_mono=_np(mono), wl_disp=_np(disp), wl_conf=_np(conf), wl_scale=_np(sc), wl_shift=_np(sh))
+    np.savez_compressed(os.path.join(HERE, "producers.npz"), **out)
+    print("producers.npz", sum(np.asarray(v).nbytes for v in out.values()) / 1e6, "MB raw")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    table = {"path_small": path_small, "model_slice": model_slice, "tiles": tiles, "reductions": reductions, "grads": grads}
+    table = {"path_small": path_small, "model_slice": model_slice, "tiles": tiles, "reductions": reductions, "grads": grads,
+             "producers": producers}
     for name in sys.argv[1:] or list(table):
         table[name]()

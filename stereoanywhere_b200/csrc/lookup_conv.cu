@@ -88,10 +88,23 @@ __global__ void __launch_bounds__(2 * kLcTile) lookup_conv_kernel(const LcArgs a
     s_blk[tid] = blk;
   }
   // weights -> K-major 8x(16 B) core matrices, rounded to tf32; channels 36..39 are zero padding
-  for (int e = tid; e < kLcN * kLcK; e += THREADS) {
-    const int n = e / kLcK, k = e % kLcK;
-    const float wv = (k < 36) ? to_tf32(__ldg(a.weight + n * 36 + k)) : 0.0f;
-    *reinterpret_cast<float*>(sB + ((n >> 3) * (kLcK / 4) + (k >> 2)) * 128 + (n & 7) * 16 + (k & 3) * 4) = wv;
+  if ((reinterpret_cast<uintptr_t>(a.weight) & 15) == 0) {
+    // one float4 (four consecutive k of one output channel) per step: 128-bit load, 4 x cvt, 128-bit store
+    for (int e = tid; e < kLcN * (kLcK / 4); e += THREADS) {
+      const int n = e / (kLcK / 4), kq = e % (kLcK / 4);
+      float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kq < 9) {
+        wv = __ldg(reinterpret_cast<const float4*>(a.weight + n * 36 + kq * 4));
+        wv = make_float4(to_tf32(wv.x), to_tf32(wv.y), to_tf32(wv.z), to_tf32(wv.w));
+      }
+      *reinterpret_cast<float4*>(sB + ((n >> 3) * (kLcK / 4) + kq) * 128 + (n & 7) * 16) = wv;
+    }
+  } else {
+    for (int e = tid; e < kLcN * kLcK; e += THREADS) {
+      const int n = e / kLcK, k = e % kLcK;
+      const float wv = (k < 36) ? to_tf32(__ldg(a.weight + n * 36 + k)) : 0.0f;
+      *reinterpret_cast<float*>(sB + ((n >> 3) * (kLcK / 4) + (k >> 2)) * 128 + (n & 7) * 16 + (k & 3) * 4) = wv;
+    }
   }
   if (tid < kLcN) s_bias[tid] = __ldg(a.bias + tid);
   if (warp == 0) {
@@ -110,17 +123,26 @@ __global__ void __launch_bounds__(2 * kLcTile) lookup_conv_kernel(const LcArgs a
 
   // ---- stage one packed line per (pixel, volume), chunk c of pixel p at chunk c ^ (p & 7)
   float* stage = reinterpret_cast<float*>(sA);
+  {  // as in lookup_packed_kernel: the 64-bit line addresses are formed once per pixel and shared by the volumes
+    constexpr int UPS = THREADS / 8, SPV = 4;  // units per step, steps per volume
+    const int ch = tid & 7, u0 = tid >> 3;
+    long long goff[SPV];
 #pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    const int idx = tid + n * THREADS;
-    const int unit = idx >> 3, ch = idx & 7;
-    const int v = unit / TILE, p = unit % TILE;
-    float* dst = stage + unit * 32 + ((ch ^ (p & 7)) << 2);
-    const int blk = s_blk[p];
-    if (blk >= 0)
-      lc_cp_async16(dst, (v ? a.packed[1] : a.packed[0]) + ((row0 + p) * a.nblk + blk) * 32 + ch * 4);
-    else
-      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = 0; m < SPV; ++m) {
+      const int pm = u0 + m * UPS;
+      const int blk = s_blk[pm];
+      goff[m] = blk >= 0 ? ((row0 + pm) * (long long)a.nblk + blk) * 32 + ch * 4 : -1;
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int v = n / SPV, m = n % SPV;
+      const int pm = u0 + m * UPS;
+      float* dst = stage + (v * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2);
+      if (goff[m] >= 0)
+        lc_cp_async16(dst, (v ? a.packed[1] : a.packed[0]) + goff[m]);
+      else
+        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -594,3 +594,41 @@ def test_training_step_gradients_vs_oracle(sa):
     want = run(O.OracleCorrBlock, O.aten_corr_volume, lambda d, cf: O.aten_truncation_mask(d, cf, 0.9), "cpu")
     for a_, b_ in zip(got, want):
         assert normwise(a_, b_) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 72, 72), (1, 2, 40, 520), (1, 1, 132, 264), (1, 2, 20, 52), (1, 2, 17, 30)])
+def test_volume_passes_vs_oracle(sa, shape):
+    """A2 / A5 / A6 / A7 standalone passes at widths that take the register-resident row kernels (W3 <= 384), the
+    streaming row kernels (W3 > 384) and the generic kernels (W3 % 4 != 0), against the oracle's ATen sequence."""
+    b, h, w2, w3 = shape
+    gen = torch.Generator().manual_seed(11 + w3)
+    nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w2, generator=gen), dim=1)
+    nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w3, generator=gen), dim=1)
+    vol = torch.randn(b, 1, h, w2, w3, generator=gen)
+    # A2
+    mono = sa.CorrBlockB200.mono_corr(nl.to(DEV), nr.to(DEV))
+    ref = 1.73 * (torch.einsum("bchw,bchv->bhwv", nl.double(), nr.double()) / float(np.float32(np.sqrt(3.0))))
+    assert mono.shape == (b, h, w2, 1, w3) and maxabs(mono.squeeze(3), ref) < 2e-6
+    # A5 (square volumes only: the reference's mask is [B,1,H,W,W])
+    if w2 == w3:
+        disp = torch.rand(b, 1, h, w2, generator=gen) * (w3 / 4)
+        conf = torch.rand(b, 1, h, w2, generator=gen)
+        t_ref = O.aten_truncation_mask(disp, conf, 0.9)
+        assert maxabs(sa.truncation_mask(disp.to(DEV), conf.to(DEV), 0.9), t_ref) < 1e-6
+        assert maxabs(sa.truncation_mask(disp.to(DEV), conf.to(DEV), 0.9, vol=vol.to(DEV)), t_ref * vol) < 1e-5
+    # A6
+    mde_l, mde_r = torch.rand(b, 1, h, w2, generator=gen), torch.rand(b, 1, h, w3, generator=gen)
+    mde_l[0, 0, 0, 0] = 1.0
+    want = O.aten_masked_volume(vol, O.aten_depth_bin_masks(mde_l, 8), O.aten_depth_bin_masks(mde_r, 8))
+    got = sa.masked_volume(vol.to(DEV), mde_l.to(DEV), mde_r.to(DEV), 8)
+    assert np.array_equal(got.cpu().numpy(), want.numpy())
+    fused = sa.masked_mono_volume(nl.to(DEV), nr.to(DEV), mde_l.to(DEV), mde_r.to(DEV), 8)
+    want_m = O.aten_masked_volume(mono.cpu().squeeze(3).unsqueeze(1), O.aten_depth_bin_masks(mde_l, 8), O.aten_depth_bin_masks(mde_r, 8))
+    assert np.array_equal(fused.cpu().numpy(), want_m.numpy())
+    # A7
+    binm = (mde_l < 0.3).to(torch.float32)
+    assert np.array_equal(sa.corrupt_volume(vol.to(DEV), binm.to(DEV), "roll", shift=7).cpu().numpy(),
+                          O.aten_corrupt_roll(vol, binm, 7).numpy())
+    noise = torch.rand(b, 1, h, w2, generator=gen)
+    assert maxabs(sa.corrupt_volume(vol.to(DEV), binm.to(DEV), "noise", noise=noise.to(DEV)),
+                  O.aten_corrupt_scale(vol, binm, noise.unsqueeze(4))) < 1e-6

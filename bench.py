@@ -597,9 +597,9 @@ def run_tiled(args):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # ncu --set full capture (profiles/); None until a capture for that workload exists.
 TRAFFIC_BYTES = {
-    # profiles/r1/lookup_packed_ncu_full_raw.csv: 60.46 MB read + 14.1 MB written while the kernel runs
+    # profiles/r1/lookup_tile64_pack_normals_ncu_summary.txt: 60.46 MB read + 13.9 MB written while the kernel runs
     # (the other ~55 MB of its 69 MB output are still dirty in L2 at kernel end and reach HBM later)
-    ("c2_kitti_375x1242_b8", "fused"): 74_560_000,
+    ("c2_kitti_375x1242_b8", "fused"): 74_360_000,
 }
 
 

@@ -632,3 +632,36 @@ def test_volume_passes_vs_oracle(sa, shape):
     noise = torch.rand(b, 1, h, w2, generator=gen)
     assert maxabs(sa.corrupt_volume(vol.to(DEV), binm.to(DEV), "noise", noise=noise.to(DEV)),
                   O.aten_corrupt_scale(vol, binm, noise.unsqueeze(4))) < 1e-6
+
+
+def test_fused_constructors_random_shapes(sa):
+    """Thirty random shapes (ragged W2 / W3, single rows, widths around the tile / chunk boundaries): the fused
+    constructors must reproduce the two-step forms bit for bit, and a lookup from them the fp64 closed form."""
+    rng = np.random.RandomState(2024)
+    B = sa.CorrBlockB200
+    B.precision = "tf32"
+    for it in range(30):
+        b, h = int(rng.randint(1, 3)), int(rng.randint(1, 5))
+        w2 = int(rng.choice([4, 8, 28, 32, 36, 124, 128, 132, 160, 252, 256, 260, 312, 388]))
+        w3 = int(rng.choice([8, 16, 24, 32, 40, 120, 128, 136, 160, 248, 256, 264, 312, 384, 392, 520]))
+        c = int(rng.choice([32, 64, 96, 128]))
+        gen = torch.Generator().manual_seed(1000 + it)
+        fl = torch.randn(b, c, h, w2, generator=gen).to(DEV)
+        fr = torch.randn(b, c, h, w3, generator=gen).to(DEV)
+        t = None
+        if it % 2:
+            t = ((torch.rand(b, 1, h, w2, generator=gen) * (w3 / 4)).to(DEV), torch.rand(b, 1, h, w2, generator=gen).to(DEV), 0.9)
+        one, two = B.from_features(fl, fr, truncate=t), B(B.corr(fl, fr), truncate=t)
+        assert torch.equal(one._packed, two._packed), (it, b, c, h, w2, w3)
+        nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w2, generator=gen), dim=1).to(DEV)
+        nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w3, generator=gen), dim=1).to(DEV)
+        mono = B.from_normals(nl, nr)
+        assert torch.equal(mono._packed, B(B.mono_corr(nl, nr))._packed), (it, b, h, w2, w3)
+        x = torch.arange(w2, dtype=torch.float32).view(1, 1, 1, w2).expand(b, 1, h, w2)
+        coords = torch.cat([x * (w3 / max(w2, 1)) - torch.rand(b, 1, h, w2, generator=gen) * (w3 / 4) + (it % 3) * 3,
+                            torch.zeros(b, 1, h, w2)], 1).to(DEV)
+        s_, m_ = B.lookup_pair(one, mono, coords)
+        levels = O.closed_pyramid(mono.fullcorr.squeeze(3).cpu().numpy(), 4)[:4]
+        ref = O.closed_lookup([lv.reshape(b, h, w2, -1) for lv in levels], coords[:, 0].cpu().numpy(), 4)
+        assert maxabs(m_, ref) < 1e-5, (it, b, h, w2, w3)
+        assert torch.equal(s_, two(coords))

@@ -84,3 +84,11 @@ def test_grad_policy():
     with pytest.raises(NotImplementedError):
         C._no_grad_check(None, t)
     C._no_grad_check(None, t.detach())
+
+
+def test_packed_row_floats_matches_library():
+    from stereoanywhere_b200 import _lib, ops
+
+    lib = _lib.load()
+    for w in (8, 40, 128, 312, 768, 1024):
+        assert ops.packed_row_floats(w) == int(lib.sa_packed_row_floats(w))

@@ -175,7 +175,8 @@ class GpuPath:
 
     def build_mono(self):
         B, d = self.sa.CorrBlockB200, self.d
-        self.launches += 1
+        if B.mono_mode != "otf":
+            self.launches += 1   # packed: one pack kernel; on the fly: nothing to launch, the lookups read the normals
         return B.from_normals(d["nl"], d["nr"], radius=RADIUS, num_levels=LEVELS)
 
     def build(self):
@@ -183,9 +184,8 @@ class GpuPath:
         B = sa.CorrBlockB200
         if self.variant == "fused":
             # stereo: corr + truncation + pyramid in the GEMM epilogue (one kernel); mono: normals -> packed
-            fs = B.from_features(d["fl"], d["fr"], radius=RADIUS, num_levels=LEVELS, truncate=(d["tdisp"], d["tconf"], 0.9))
-            fm = B.from_normals(d["nl"], d["nr"], radius=RADIUS, num_levels=LEVELS)
-            self.launches += 2
+            fs = self.build_stereo()
+            fm = self.build_mono()
         else:  # strict reference protocol, op for op (stereoanywhere.py:135-136, 203, 253-259)
             vs = B.corr(d["fl"], d["fr"]).squeeze(3).unsqueeze(1)
             vm = 1.73 * B.corr(d["nl"], d["nr"]).squeeze(3).unsqueeze(1)
@@ -239,6 +239,8 @@ def run_gpu(args):
     import stereoanywhere_b200 as sa
 
     sa.CorrBlockB200.precision = args.precision
+    sa.CorrBlockB200.mono_mode = args.mono
+    otf = args.variant == "fused" and args.mono == "otf"
     b, c, h, w = WORKLOADS[args.workload]
     host, d = make_inputs(b, c, h, w, dev, seed=rank, pinned=True)
     torch.cuda.synchronize()
@@ -289,7 +291,11 @@ def run_gpu(args):
         torch.cuda.synchronize()
         seq = path.coords_seq()
         g_build, g_look = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        if args.variant == "fused":
+        if otf:
+            with torch.cuda.graph(g_build):
+                fs = path.build_stereo()
+            fm = path.build_mono()   # holds the normal maps only: no kernel, nothing to capture
+        elif args.variant == "fused":
             g_mono = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_build):
                 fs = path.build_stereo()
@@ -330,12 +336,14 @@ def run_gpu(args):
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    launches = path.launches if g_build is None else args.steps * (34 if args.variant == "fused" else 69)
+    launches = path.launches if g_build is None else args.steps * ((33 if otf else 34) if args.variant == "fused" else 69)
     lk_ms = sum(a.elapsed_time(bb) for a, bb in lk_events) / args.steps
     breakdown = None
-    if g_mono is not None:  # fused variant under graphs: one kernel per graph for the two builders
+    if g_build is not None and args.variant == "fused":  # one kernel per graph for the builders
         st_ms = sum(a.elapsed_time(bb) for a, bb in bd_events) / args.steps
-        mo_ms = sum(bd_events[k][1].elapsed_time(lk_events[k][0]) for k in range(args.steps)) / args.steps
+        mo_ms = None
+        if g_mono is not None:
+            mo_ms = sum(bd_events[k][1].elapsed_time(lk_events[k][0]) for k in range(args.steps)) / args.steps
         breakdown = (st_ms, mo_ms)
     n_lk_launch = ITERS if args.variant == "fused" else 2 * ITERS
     lk_launch_ms = lk_ms / n_lk_launch
@@ -404,16 +412,22 @@ def run_gpu(args):
     if rank == 0:
         peak, peak_src = load_peaks()
         p = b * h * w
-        alg = (612 if args.variant == "fused" else 308) * p
+        # algorithmic bytes per pixel and launch: coords 4 + 160 per volume of windows + 144 per volume of
+        # outputs.  With the mono volume computed on the fly its 160 B of windows are not memory traffic any more.
+        alg_px = (452 if otf else 612) if args.variant == "fused" else 308
+        real_px = (416 if otf else 544)
+        alg = alg_px * p
         achieved = alg / (lk_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "lookup_packed_kernel" + ("<NV=2>" if args.variant == "fused" else "<NV=1>"),
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": TRAFFIC_BYTES.get((args.workload, args.variant)), "peak_source": peak_src,
+                "traffic": TRAFFIC_BYTES.get((args.workload, args.variant, args.mono)), "peak_source": peak_src,
+                "algorithmic_bytes_per_pixel": alg_px,
                 "algorithmic_bytes_per_launch": alg, "launch_us": round(lk_launch_ms * 1e3, 2),
                 "path_algorithmic_gbs": round(path_bytes(b, c, h, w) / (ms_step * 1e-3) / 1e9, 1)}
         kernels = None
         if breakdown is not None:
-            st_us, mo_us = breakdown[0] * 1e3, breakdown[1] * 1e3
+            st_us = breakdown[0] * 1e3
+            mo_us = breakdown[1] * 1e3 if breakdown[1] is not None else None
             packed = p * (w // 8 + 9) * 128
             tf32_peak = tensor_peak_tf32()
             tflops = 2.0 * p * w * c / (st_us * 1e-6) / 1e12
@@ -423,10 +437,13 @@ def run_gpu(args):
                                    "tflops": round(tflops, 1), "tensor_peak_tf32": tf32_peak,
                                    "tensor_frac": round(tflops / tf32_peak, 4),
                                    "note": "HBM-bound by the packed write; the tensor pipe is reported, not targeted"},
-                "pack_normals": {"us": round(mo_us, 1), "hbm_gbs": round(packed / mo_us / 1e3, 1), "hbm_frac": round(packed / mo_us / 1e3 / peak, 4)},
+                "pack_normals": ({"us": round(mo_us, 1), "hbm_gbs": round(packed / mo_us / 1e3, 1),
+                                  "hbm_frac": round(packed / mo_us / 1e3 / peak, 4)} if mo_us is not None else
+                                 "not launched: the mono lookups are computed from the normal maps inside the lookup kernel"),
                 "lookup_packed2": {"us": round(lk_launch_ms * 1e3, 2), "launches": n_lk_launch,
-                                   "hbm_gbs_real_bytes": round(544 * p / (lk_launch_ms * 1e-3) / 1e9, 1),
-                                   "hbm_frac_real_bytes": round(544 * p / (lk_launch_ms * 1e-3) / 1e9 / peak, 4)},
+                                   "real_bytes_per_pixel": real_px,
+                                   "hbm_gbs_real_bytes": round(real_px * p / (lk_launch_ms * 1e-3) / 1e9, 1),
+                                   "hbm_frac_real_bytes": round(real_px * p / (lk_launch_ms * 1e-3) / 1e9 / peak, 4)},
             }
         cpu = None if args.no_cpu_baseline else cpu_baseline(args.workload, sample_pairs=args.cpu_pairs, reps=3)
         result = {
@@ -436,6 +453,8 @@ def run_gpu(args):
             "data": "synthetic (seeded N(0,1) features, unit normals, U(0,W/4) disparities)",
             "config": {"workload": args.workload, "pairs_per_gpu": b, "C": c, "H4": h, "W4": w, "iters": ITERS,
                        "levels": LEVELS, "radius": RADIUS, "variant": args.variant, "cuda_graph": bool(args.graph),
+                       "mono": ("on the fly: lookups computed from the normal maps inside the lookup kernel, bit-identical to "
+                                "the packed pyramid (no mono volume / pyramid in memory)") if otf else "packed pyramid",
                        "l2": "inputs+volumes (>1 GB/step) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"batch-sharded x{world}, async all_gather of quarter-res disparity per step"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -478,6 +497,7 @@ def run_tiled(args):
     from stereoanywhere_b200 import tiling
 
     sa.CorrBlockB200.precision = args.precision
+    sa.CorrBlockB200.mono_mode = args.mono
     B = sa.CorrBlockB200
     H, W = 1984, 2880                      # 1984x2872 replicate-padded to /32 (test_mapreduce_v2.py:217-227)
     th, tw, ov = tiling.PRESETS[args.tile_preset]
@@ -599,7 +619,7 @@ def run_tiled(args):
 TRAFFIC_BYTES = {
     # profiles/r1/lookup_tile64_pack_normals_ncu_summary.txt: 60.46 MB read + 13.9 MB written while the kernel runs
     # (the other ~55 MB of its 69 MB output are still dirty in L2 at kernel end and reach HBM later)
-    ("c2_kitti_375x1242_b8", "fused"): 74_360_000,
+    ("c2_kitti_375x1242_b8", "fused", "packed"): 74_360_000,
 }
 
 
@@ -678,6 +698,8 @@ def main():
     ap.add_argument("--variant", default="fused", choices=["fused", "protocol"],
                     help="fused: truncate= / mono_corr / lookup_pair entry points; protocol: the reference's exact call sequence")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"], help="stereo correlation kernel")
+    ap.add_argument("--mono", default="packed", choices=["otf", "packed"],
+                    help="mono block of the fused variant: lookups computed on the fly from the normals, or the packed pyramid")
     ap.add_argument("--graph", type=int, default=1, help="replay the step from a CUDA graph in the device-resident run")
     ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -126,6 +126,15 @@ int sa_pack_pyramid_normals(const float* normals_l, const float* normals_r, floa
 int sa_lookup_packed(const float* packed_a, const float* packed_b, int W3, const float* coords,
                      int64_t coords_bstride, float* out_a, float* out_b, int B, int H, int W, void* stream);
 
+/* Lookup with the MONO volume computed on the fly from the C = 3 normal maps (stereoanywhere.py:136 when the
+ * volume is looked up as it is): the thread of a (pixel, mono) pair forms the 80 level-0 values its packed line
+ * is made of and pools them - bit-identical to sa_pack_pyramid_normals + sa_lookup_packed, with no packed mono
+ * array at all.  packed_a / out_a: an ordinary packed volume looked up in the same launch (both NULL: mono only).
+ * normals_l is [B,3,H,W], normals_r [B,3,H,W3]; divisor / post_scale as in sa_corr_fp32. */
+int sa_lookup_packed_normals(const float* packed_a, const float* normals_l, const float* normals_r, float divisor,
+                             float post_scale, int W3, const float* coords, int64_t coords_bstride, float* out_a,
+                             float* out_mono, int B, int H, int W, void* stream);
+
 /* ---------------------------------------------------------------- A1 + A5 + A3 fused (tensor cores -> packed pyramid)
  * packed = sa_pack_pyramid(T * sa_corr_tf32(L, R)) in ONE kernel: the truncation product and the avg-pooled
  * pyramid are formed in the GEMM epilogue (TMEM -> registers -> packed lines -> TMA store); the fp32 volume

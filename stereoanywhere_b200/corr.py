@@ -176,8 +176,25 @@ class CorrBlockB200:
         self._widths = ops.level_widths(w3, num_levels)
         self._levels = None
         self._dlevels, self._handle = None, None
-        self._packed = _OPS.pack_pyramid_normals(self._normals[0], self._normals[1], float(gain))
+        self._packed = None
+        self._otf = cls.mono_mode == "otf"  # on-the-fly lookups (see mono_mode)
+        if not self._otf:
+            self._packed = _OPS.pack_pyramid_normals(self._normals[0], self._normals[1], float(gain))
         return self
+
+    #: how a block built by `from_normals` serves its lookups: "packed" (default) writes the packed pyramid once
+    #: (241 us at KITTI size, batch 8) and every lookup reads one line; "otf" keeps only the normal maps and
+    #: computes every lookup inside the lookup kernel - bit-identical, no 1.5 GB packed array, but 44.6 us instead
+    #: of 23.3 us per dual lookup (80 three-channel dot products per pixel), i.e. a memory-saving mode, not a
+    #: faster one for 32 iterations.  SA_B200_MONO overrides the default.
+    mono_mode = os.environ.get("SA_B200_MONO", "packed")
+
+    def _ensure_packed(self) -> torch.Tensor:
+        """The packed pyramid of this block (built on demand for on-the-fly mono blocks)."""
+        if self._packed is None and getattr(self, "_otf", False):
+            self._packed = _OPS.pack_pyramid_normals(self._normals[0], self._normals[1], self._normals[2])
+            self._otf = False
+        return self._packed
 
     @classmethod
     def from_features(cls, fmap2: torch.Tensor, fmap3: torch.Tensor, num_levels: int = 4, radius: int = 4, *,
@@ -242,6 +259,8 @@ class CorrBlockB200:
         return [lv[:, :w].unsqueeze(1).unsqueeze(1) for lv, w in zip(self._build_levels(), self._widths)]
 
     def _lookup_nograd(self, coords: torch.Tensor) -> torch.Tensor:
+        if getattr(self, "_otf", False):
+            return _OPS.lookup_normals(self._normals[0], self._normals[1], self._normals[2], coords)
         if self._packed is not None:
             return _OPS.lookup_packed(self._packed, self._shape[3], coords)
         return _OPS.lookup(self._levels, self._widths, coords, self.radius, self.pad[0], self.pad[1])
@@ -291,14 +310,18 @@ class CorrBlockB200:
         _no_grad_check(coords)
         if torch.is_grad_enabled() and (block_a._handle is not None or block_b._handle is not None):
             return block_a(coords), block_b(coords)  # training: each lookup is its own autograd node
+        otf_b = getattr(block_b, "_otf", False)
         if (block_a.radius != block_b.radius or block_a._widths != block_b._widths
-                or block_a.pad != [0, 0] or block_b.pad != [0, 0]
-                or (block_a._packed is None) != (block_b._packed is None)):
+                or block_a.pad != [0, 0] or block_b.pad != [0, 0] or getattr(block_a, "_otf", False)
+                or (block_a._packed is None) != (block_b._packed is None and not otf_b)):
             return block_a(coords), block_b(coords)
         dt = coords.dtype
         if dt != torch.float32:
             coords = coords.float()
-        if block_a._packed is not None:
+        if block_a._packed is not None and getattr(block_b, "_otf", False):
+            oa, ob = _OPS.lookup_packed_normals2(block_a._packed, block_b._normals[0], block_b._normals[1],
+                                                 block_b._normals[2], coords)
+        elif block_a._packed is not None:
             oa, ob = _OPS.lookup_packed2(block_a._packed, block_b._packed, block_a._shape[3], coords)
         else:
             oa, ob = _OPS.lookup2(block_a._levels, block_b._levels, block_a._widths, coords, block_a.radius)
@@ -312,6 +335,8 @@ def lookup_pair_convc1(block_a: CorrBlockB200, block_b: CorrBlockB200, coords: t
     into the lookups of stereoanywhere.py:270-271.  TF32 tensor-core product, fp32 accumulate.
     Falls back to two lookups + torch convolutions when the blocks are not in the packed layout."""
     _no_grad_check(coords, weight, bias)
+    block_a._ensure_packed()
+    block_b._ensure_packed()  # an on-the-fly mono block is packed on first use here
     if (block_a._packed is None or block_b._packed is None or block_a._shape != block_b._shape
             or weight.shape[0] != 64 or weight.shape[1] != 36):
         sa_, sb_ = CorrBlockB200.lookup_pair(block_a, block_b, coords)

@@ -206,6 +206,11 @@ struct PLookupArgs {
   const float* coords;
   long long coords_bstride;
   int HW, W3, nblk;
+  // on-the-fly mono volume (OTF >= 0): unit normals [B,3,H,Wimg] / [B,3,H,W3], A2's divisor and post_scale
+  const float* nl;
+  const float* nr;
+  int H, Wimg;
+  float divisor, inv_divisor, post_scale;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -220,7 +225,13 @@ __device__ __forceinline__ void shift_if(float (&v)[N], bool on, int by, int kee
     if (i < keep && i + by < N) v[i] = on ? v[i + by] : v[i];
 }
 
-template <int NV, int TILE>
+// OTF = index of a volume that is not read from a packed array but COMPUTED from the C = 3 normal maps (the mono
+// volume of stereoanywhere.py:136 when it is looked up as it is, i.e. use_aggregate_mono_vol off), or -1.  The
+// thread of such a (pixel, volume) forms the 80 level-0 values L0[8q-32 .. 8q+47] its line is made of - three
+// FMAs, the division and the 1.73 scale in pack_kernel<normals>'s order - and pools them with the pyramid's own
+// 0.5 (a + b): exactly the 17 + 13 + 11 + 10 window entries the packed path holds after its derivation step, bit
+// for bit.  ~900 instructions per pixel instead of a 128-byte line read, and no mono pack pass at all.
+template <int NV, int TILE, int OTF>
 __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupArgs a) {
   constexpr int THREADS = NV * TILE;
   constexpr int NC = 36;
@@ -271,6 +282,7 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       const int v = n / SPV, m = n % SPV;  // compile-time
+      if (v == OTF) continue;
       const int pm = u0 + m * UPS;
       float* dst = buf + (v * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2);
       if (goff[m] >= 0)
@@ -283,35 +295,97 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
-  // ---- thread (pixel p, volume v): its line -> registers
+  // ---- thread (pixel p, volume v): the window entries of the four levels
   const int p = tid % TILE, v = tid / TILE;
-  float l0[17 + 3], e[12];  // l0: slots 0..19 (17 L0 values + 3 spill-over), e: slots 20..31
-  {
+  float l0[17], l1[13], l2[11], l3[10];  // L0[8q-4..8q+12], L1[4q-4..4q+8], L2[2q-4..2q+6], L3[q-4..q+5]
+  if (OTF >= 0 && v == OTF) {
+#pragma unroll
+    for (int i = 0; i < 17; ++i) l0[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) l1[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 11; ++i) l2[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) l3[i] = 0.f;
+    const int blk = s_blk[p];
+    if (blk >= 0) {
+      const int c0 = 8 * (blk + kQMin) - 32;
+      const int hw = hw0 + p;
+      const int hh = hw / a.Wimg, w2 = hw - hh * a.Wimg;
+      const long long plane2 = (long long)a.H * a.Wimg, plane3 = (long long)a.H * a.W3;
+      const float* nlp = a.nl + ((long long)b * 3 * a.H + hh) * a.Wimg + w2;
+      const float n0 = __ldg(nlp), n1 = __ldg(nlp + plane2), n2 = __ldg(nlp + 2 * plane2);
+      const float* nrp = a.nr + ((long long)b * 3 * a.H + hh) * a.W3;
+#pragma unroll
+      for (int m = 0; m < 10; ++m) {
+        const int col = c0 + 8 * m;
+        float g[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = 0.f;
+        if (col >= 0 && col < a.W3) {  // W3 % 8 == 0: a group of 8 columns is inside or outside as a whole
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            // (__fmul_rn: the product must be rounded on its own, as it is when pack_kernel stores the value - the
+          // compiler would otherwise contract it into the pooling adds below)
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(nrp + col + 4 * hlf));
+            const float4 r1 = __ldg(reinterpret_cast<const float4*>(nrp + plane3 + col + 4 * hlf));
+            const float4 r2 = __ldg(reinterpret_cast<const float4*>(nrp + 2 * plane3 + col + 4 * hlf));
+            g[4 * hlf + 0] = __fmul_rn(div_const(fmaf(n2, r2.x, fmaf(n1, r1.x, fmaf(n0, r0.x, 0.f))), a.divisor, a.inv_divisor), a.post_scale);
+            g[4 * hlf + 1] = __fmul_rn(div_const(fmaf(n2, r2.y, fmaf(n1, r1.y, fmaf(n0, r0.y, 0.f))), a.divisor, a.inv_divisor), a.post_scale);
+            g[4 * hlf + 2] = __fmul_rn(div_const(fmaf(n2, r2.z, fmaf(n1, r1.z, fmaf(n0, r0.z, 0.f))), a.divisor, a.inv_divisor), a.post_scale);
+            g[4 * hlf + 3] = __fmul_rn(div_const(fmaf(n2, r2.w, fmaf(n1, r1.w, fmaf(n0, r0.w, 0.f))), a.divisor, a.inv_divisor), a.post_scale);
+          }
+        }
+        const float a10 = (g[0] + g[1]) * 0.5f, a11 = (g[2] + g[3]) * 0.5f, a12 = (g[4] + g[5]) * 0.5f, a13 = (g[6] + g[7]) * 0.5f;
+        const float a20 = (a10 + a11) * 0.5f, a21 = (a12 + a13) * 0.5f;
+        l3[m] = (a20 + a21) * 0.5f;                         // L3[q-4+m]
+        if (m >= 2 && m <= 7) {                              // L2[2q-8+2m+j] -> index 2(m-2)+j of l2
+          l2[2 * (m - 2)] = a20;
+          if (2 * (m - 2) + 1 < 11) l2[2 * (m - 2) + 1] = a21;
+        }
+        if (m >= 3 && m <= 6) {                              // L1[4q-16+4m+j] -> index 4(m-3)+j of l1
+          const float a1v[4] = {a10, a11, a12, a13};
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (4 * (m - 3) + j < 13) l1[4 * (m - 3) + j] = a1v[j];
+        }
+        if (m == 3) {                                        // L0[8q-8+j], j = 4..7 -> l0[0..3]
+#pragma unroll
+          for (int j = 4; j < 8; ++j) l0[j - 4] = g[j];
+        } else if (m == 4) {                                 // L0[8q+j] -> l0[4..11]
+#pragma unroll
+          for (int j = 0; j < 8; ++j) l0[4 + j] = g[j];
+        } else if (m == 5) {                                 // L0[8q+8+j], j = 0..4 -> l0[12..16]
+#pragma unroll
+          for (int j = 0; j < 5; ++j) l0[12 + j] = g[j];
+        }
+      }
+    }
+  } else {
+    float e[15];  // slots 17..31 of the line
     const float* src = buf + tid * 32;  // unit index == tid
+    float ln[32];
 #pragma unroll
-    for (int ch = 0; ch < 5; ++ch) {
+    for (int ch = 0; ch < 8; ++ch) {
       const float4 t = *reinterpret_cast<const float4*>(src + ((ch ^ (p & 7)) << 2));
-      l0[4 * ch] = t.x; l0[4 * ch + 1] = t.y; l0[4 * ch + 2] = t.z; l0[4 * ch + 3] = t.w;
+      ln[4 * ch] = t.x; ln[4 * ch + 1] = t.y; ln[4 * ch + 2] = t.z; ln[4 * ch + 3] = t.w;
     }
 #pragma unroll
-    for (int ch = 5; ch < 8; ++ch) {
-      const float4 t = *reinterpret_cast<const float4*>(src + ((ch ^ (p & 7)) << 2));
-      e[4 * (ch - 5)] = t.x; e[4 * (ch - 5) + 1] = t.y; e[4 * (ch - 5) + 2] = t.z; e[4 * (ch - 5) + 3] = t.w;
-    }
+    for (int i = 0; i < 17; ++i) l0[i] = ln[i];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) e[i] = ln[17 + i];
+    // full windows of levels 1..3 (relative index 0 = first stored entry of the level)
+    l1[0] = e[0]; l1[1] = e[1]; l1[10] = e[2]; l1[11] = e[3]; l1[12] = e[4];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) l1[2 + t] = (l0[2 * t] + l0[2 * t + 1]) * 0.5f;
+    l2[0] = e[5]; l2[1] = e[6]; l2[8] = e[7]; l2[9] = e[8]; l2[10] = e[9];
+#pragma unroll
+    for (int t = 0; t < 6; ++t) l2[2 + t] = (l1[2 * t] + l1[2 * t + 1]) * 0.5f;
+    l3[0] = e[10]; l3[1] = e[11]; l3[7] = e[12]; l3[8] = e[13]; l3[9] = e[14];
+#pragma unroll
+    for (int t = 0; t < 5; ++t) l3[2 + t] = (l2[2 * t] + l2[2 * t + 1]) * 0.5f;
   }
   __syncthreads();  // staging is dead: `buf` becomes the [channel][pixel] output tile
-
-  // full windows of levels 1..3 (relative index 0 = first stored entry of the level)
-  float l1[13], l2[11], l3[10];
-  l1[0] = l0[17]; l1[1] = l0[18]; l1[10] = l0[19]; l1[11] = e[0]; l1[12] = e[1];
-#pragma unroll
-  for (int t = 0; t < 8; ++t) l1[2 + t] = (l0[2 * t] + l0[2 * t + 1]) * 0.5f;
-  l2[0] = e[2]; l2[1] = e[3]; l2[8] = e[4]; l2[9] = e[5]; l2[10] = e[6];
-#pragma unroll
-  for (int t = 0; t < 6; ++t) l2[2 + t] = (l1[2 * t] + l1[2 * t + 1]) * 0.5f;
-  l3[0] = e[7]; l3[1] = e[8]; l3[7] = e[9]; l3[8] = e[10]; l3[9] = e[11];
-#pragma unroll
-  for (int t = 0; t < 5; ++t) l3[2 + t] = (l2[2 * t] + l2[2 * t + 1]) * 0.5f;
 
   const float x = s_x[p];
   const float flx = fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
@@ -387,12 +461,12 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
   }
 }
 
-template <int NV, int TILE>
+template <int NV, int TILE, int OTF>
 static int launch_packed_t(const PLookupArgs& a, int B, cudaStream_t st) {
   constexpr int NC = 36, SP = TILE + 4;
   constexpr int buf_floats = (NV * TILE * 32 > NV * NC * SP) ? NV * TILE * 32 : NV * NC * SP;
   const size_t smem = (size_t)(buf_floats + 2 * TILE) * sizeof(float);
-  auto kern = lookup_packed_kernel<NV, TILE>;
+  auto kern = lookup_packed_kernel<NV, TILE, OTF>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) SA_FAIL((int)e, "sa_lookup_packed: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -402,14 +476,14 @@ static int launch_packed_t(const PLookupArgs& a, int B, cudaStream_t st) {
   return finish_launch("sa_lookup_packed");
 }
 
-template <int NV>
+template <int NV, int OTF>
 static int launch_packed(const PLookupArgs& a, int B, cudaStream_t st) {
   static const int tile = getenv("SA_B200_LOOKUP_TILE") ? atoi(getenv("SA_B200_LOOKUP_TILE")) : 64;
   // pixels per CTA: 64 measured best at c2 (23.2 us per dual lookup; 128: 24.2, 32: 23.5) - smaller CTAs
   // shorten the tail of the last wave and raise the number of lines in flight per SM
-  if (tile == 32) return launch_packed_t<NV, 32>(a, B, st);
-  if (tile == 128) return launch_packed_t<NV, 128>(a, B, st);
-  return launch_packed_t<NV, 64>(a, B, st);
+  if (tile == 32) return launch_packed_t<NV, 32, OTF>(a, B, st);
+  if (tile == 128) return launch_packed_t<NV, 128, OTF>(a, B, st);
+  return launch_packed_t<NV, 64, OTF>(a, B, st);
 }
 
 }  // namespace sa
@@ -482,5 +556,30 @@ extern "C" int sa_lookup_packed(const float* packed_a, const float* packed_b, in
   a.out[0] = out_a; a.out[1] = out_b;
   a.coords = coords; a.coords_bstride = coords_bstride;
   a.HW = H * W; a.W3 = W3; a.nblk = packed_blocks(W3);
-  return packed_b ? launch_packed<2>(a, B, (cudaStream_t)stream) : launch_packed<1>(a, B, (cudaStream_t)stream);
+  return packed_b ? launch_packed<2, -1>(a, B, (cudaStream_t)stream) : launch_packed<1, -1>(a, B, (cudaStream_t)stream);
+}
+
+extern "C" int sa_lookup_packed_normals(const float* packed_a, const float* normals_l, const float* normals_r, float divisor,
+                                        float post_scale, int W3, const float* coords, int64_t coords_bstride,
+                                        float* out_a, float* out_mono, int B, int H, int W, void* stream) {
+  using namespace sa;
+  SA_REQUIRE(normals_l && normals_r && coords && out_mono, SA_E_INVALID, "sa_lookup_packed_normals: null pointer");
+  SA_REQUIRE((packed_a == nullptr) == (out_a == nullptr), SA_E_INVALID, "sa_lookup_packed_normals: packed_a / out_a must come together");
+  SA_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 31) && divisor != 0.f, SA_E_INVALID,
+             "sa_lookup_packed_normals: bad sizes");
+  SA_REQUIRE(W3 >= 8 && W3 % 8 == 0, SA_E_UNSUPPORTED, "sa_lookup_packed_normals: W3 must be a multiple of 8");
+  SA_REQUIRE(aligned16(normals_r) && aligned16(out_mono) && (!packed_a || (aligned16(packed_a) && aligned16(out_a))), SA_E_ALIGN,
+             "sa_lookup_packed_normals: pointers must be 16-byte aligned");
+  (void)num_sms();
+  PLookupArgs a = {};
+  a.coords = coords; a.coords_bstride = coords_bstride;
+  a.HW = H * W; a.W3 = W3; a.nblk = packed_blocks(W3);
+  a.nl = normals_l; a.nr = normals_r; a.H = H; a.Wimg = W;
+  a.divisor = divisor; a.inv_divisor = (float)(1.0 / (double)divisor); a.post_scale = post_scale;
+  if (packed_a) {
+    a.packed[0] = packed_a; a.out[0] = out_a; a.out[1] = out_mono;
+    return launch_packed<2, 1>(a, B, (cudaStream_t)stream);
+  }
+  a.out[0] = out_mono;
+  return launch_packed<1, 0>(a, B, (cudaStream_t)stream);
 }

@@ -383,6 +383,42 @@ def _lookup_packed(packed_a: torch.Tensor, packed_b: Optional[torch.Tensor], w3:
     return out_a, out_b
 
 
+def _lookup_normals(packed_a: Optional[torch.Tensor], normals_l: torch.Tensor, normals_r: torch.Tensor, post_scale: float,
+                    coords: torch.Tensor):
+    """Lookup with the mono volume computed on the fly from the normal maps (csrc/packed.cu, OTF path); with
+    `packed_a` the stereo volume is looked up in the same launch.  Returns (out_a or None, out_mono)."""
+    coords, b, h, w = _coords_view(coords)
+    _cuda_f32(normals_l, "normals_l")
+    _cuda_f32(normals_r, "normals_r")
+    _req(normals_l.shape == (b, 3, h, w) and normals_r.shape[:3] == (b, 3, h), "normals must be [B,3,H,W] matching coords")
+    w3 = normals_r.shape[3]
+    _req(w3 >= 8 and w3 % 8 == 0, "on-the-fly mono lookup needs W3 % 8 == 0")
+    normals_l, normals_r = normals_l.contiguous(), normals_r.contiguous()
+    out_m = torch.empty((b, 36, h, w), dtype=torch.float32, device=coords.device)
+    out_a = None
+    if packed_a is not None:
+        _cuda_f32(packed_a, "packed pyramid")
+        _req(packed_a.shape == (b * h * w, packed_row_floats(w3)), "coords do not match the packed volume")
+        out_a = torch.empty_like(out_m)
+    lib = _lib.load()
+    divisor = float(torch.sqrt(torch.tensor(3)))
+    with _on(coords.device):
+        rc = lib.sa_lookup_packed_normals(packed_a.data_ptr() if packed_a is not None else None, normals_l.data_ptr(),
+                                          normals_r.data_ptr(), divisor, float(post_scale), w3, coords.data_ptr(),
+                                          coords.stride(0), out_a.data_ptr() if out_a is not None else None,
+                                          out_m.data_ptr(), b, h, w, _stream_ptr(coords))
+    _lib.check(rc, "sa_lookup_packed_normals")
+    return out_a, out_m
+
+
+def _lookup_normals1(normals_l, normals_r, post_scale, coords):
+    return _lookup_normals(None, normals_l, normals_r, post_scale, coords)[1]
+
+
+def _lookup_packed_normals2(packed_a, normals_l, normals_r, post_scale, coords):
+    return _lookup_normals(packed_a, normals_l, normals_r, post_scale, coords)
+
+
 def _lookup_packed_conv(packed_a: torch.Tensor, packed_b: torch.Tensor, w3: int, coords: torch.Tensor,
                         weight: torch.Tensor, bias: torch.Tensor):
     """relu(convc1(lookup_a)), relu(convc1(lookup_b)) without materialising the lookups (csrc/lookup_conv.cu)."""
@@ -504,6 +540,8 @@ _LIBDEF.define("pack_pyramid_normals(Tensor normals_l, Tensor normals_r, float p
 _LIBDEF.define("corr_pack(Tensor fmap_l, Tensor fmap_r, Tensor? trunc_disp, Tensor? trunc_conf, float trunc_gain) -> Tensor")
 _LIBDEF.define("volume_softargmax(Tensor vol) -> (Tensor, Tensor)")
 _LIBDEF.define("volume_entropy_conf(Tensor vol) -> (Tensor, Tensor)")
+_LIBDEF.define("lookup_normals(Tensor normals_l, Tensor normals_r, float post_scale, Tensor coords) -> Tensor")
+_LIBDEF.define("lookup_packed_normals2(Tensor packed_a, Tensor normals_l, Tensor normals_r, float post_scale, Tensor coords) -> (Tensor, Tensor)")
 _LIBDEF.define("lookup_packed(Tensor packed, int w3, Tensor coords) -> Tensor")
 _LIBDEF.define("lookup_packed2(Tensor packed_a, Tensor packed_b, int w3, Tensor coords) -> (Tensor, Tensor)")
 _LIBDEF.define("lookup_packed_conv(Tensor packed_a, Tensor packed_b, int w3, Tensor coords, Tensor weight, Tensor bias) -> (Tensor, Tensor)")
@@ -520,6 +558,8 @@ _LIBDEF.impl("pack_pyramid_normals", _pack_pyramid_normals, "CUDA")
 _LIBDEF.impl("corr_pack", _corr_pack, "CUDA")
 _LIBDEF.impl("volume_softargmax", _volume_softargmax, "CUDA")
 _LIBDEF.impl("volume_entropy_conf", _volume_entropy_conf, "CUDA")
+_LIBDEF.impl("lookup_normals", _lookup_normals1, "CUDA")
+_LIBDEF.impl("lookup_packed_normals2", _lookup_packed_normals2, "CUDA")
 _LIBDEF.impl("lookup_packed", _lookup_packed1, "CUDA")
 _LIBDEF.impl("lookup_packed2", _lookup_packed2, "CUDA")
 _LIBDEF.impl("lookup_packed_conv", _lookup_packed_conv, "CUDA")
@@ -527,5 +567,5 @@ _LIBDEF.impl("truncate", _truncate, "CUDA")
 _LIBDEF.impl("masked_volume", _masked_volume, "CUDA")
 _LIBDEF.impl("corrupt", _corrupt, "CUDA")
 
-OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "corr_pack", "volume_softargmax", "volume_entropy_conf", "lookup_packed", "lookup_packed2", "lookup_packed_conv",
+OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "corr_pack", "lookup_normals", "lookup_packed_normals2", "volume_softargmax", "volume_entropy_conf", "lookup_packed", "lookup_packed2", "lookup_packed_conv",
             "truncate", "masked_volume", "corrupt"]

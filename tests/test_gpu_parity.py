@@ -263,11 +263,11 @@ def test_from_normals_equals_mono_corr_block(sa, golden_path):
         nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w, generator=gen), dim=1).to(DEV)
         fused = B.from_normals(nl, nr)
         two = B(B.mono_corr(nl, nr))
-        assert fused._packed is not None and torch.equal(fused._packed, two._packed)
-        assert torch.equal(fused.fullcorr, two.fullcorr)
         x = torch.arange(w, dtype=torch.float32).view(1, 1, 1, w).expand(b, 1, h, w)
         coords = torch.cat([x - torch.rand(b, 1, h, w, generator=gen) * (w / 4), torch.zeros(b, 1, h, w)], 1).to(DEV)
         assert torch.equal(fused(coords), two(coords))
+        assert torch.equal(fused._ensure_packed(), two._packed)
+        assert torch.equal(fused.fullcorr, two.fullcorr)
     g = golden_path
     blk = B.from_normals(G(g["a2_nl"]), G(g["a2_nr"]))
     assert normwise(blk.fullcorr, g["a2_vol"]) < 2e-6
@@ -373,7 +373,7 @@ def test_full_size_properties(sa, cfg):
     del one, two
     nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w, device=DEV, generator=gen), dim=1)
     nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w, device=DEV, generator=gen), dim=1)
-    assert torch.equal(sa.CorrBlockB200.from_normals(nl, nr)._packed, sa.CorrBlockB200(sa.CorrBlockB200.mono_corr(nl, nr))._packed)
+    assert torch.equal(sa.CorrBlockB200.from_normals(nl, nr)._ensure_packed(), sa.CorrBlockB200(sa.CorrBlockB200.mono_corr(nl, nr))._packed)
 
 
 def test_lookup_fused_with_convc1(sa):
@@ -499,7 +499,7 @@ def test_pack_normals_matches_two_step(sa, shape):
     B = sa.CorrBlockB200
     fused = B.from_normals(nl, nr)
     two = B(B.mono_corr(nl, nr))
-    assert fused._packed is not None and torch.equal(fused._packed, two._packed)
+    assert torch.equal(fused._ensure_packed(), two._packed)
     x = torch.arange(w2, dtype=torch.float32).view(1, 1, 1, w2).expand(b, 1, h, w2)
     coords = torch.cat([x - torch.rand(b, 1, h, w2, generator=gen) * (w3 / 4), torch.zeros(b, 1, h, w2)], 1).to(DEV)
     assert torch.equal(fused(coords), two(coords))
@@ -656,7 +656,7 @@ def test_fused_constructors_random_shapes(sa):
         nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w2, generator=gen), dim=1).to(DEV)
         nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w3, generator=gen), dim=1).to(DEV)
         mono = B.from_normals(nl, nr)
-        assert torch.equal(mono._packed, B(B.mono_corr(nl, nr))._packed), (it, b, h, w2, w3)
+        assert torch.equal(mono._ensure_packed(), B(B.mono_corr(nl, nr))._packed), (it, b, h, w2, w3)
         x = torch.arange(w2, dtype=torch.float32).view(1, 1, 1, w2).expand(b, 1, h, w2)
         coords = torch.cat([x * (w3 / max(w2, 1)) - torch.rand(b, 1, h, w2, generator=gen) * (w3 / 4) + (it % 3) * 3,
                             torch.zeros(b, 1, h, w2)], 1).to(DEV)
@@ -665,3 +665,41 @@ def test_fused_constructors_random_shapes(sa):
         ref = O.closed_lookup([lv.reshape(b, h, w2, -1) for lv in levels], coords[:, 0].cpu().numpy(), 4)
         assert maxabs(m_, ref) < 1e-5, (it, b, h, w2, w3)
         assert torch.equal(s_, two(coords))
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 312, 312), (1, 3, 128, 128), (1, 2, 40, 40), (1, 2, 132, 264), (1, 1, 388, 520), (1, 2, 8, 8)])
+def test_mono_lookup_on_the_fly_is_bit_identical(sa, shape):
+    """`from_normals` blocks serve their lookups from the normal maps inside the lookup kernel (no packed mono
+    array): same bits as the packed path, alone and paired with a packed stereo block, borders included."""
+    b, h, w2, w3 = shape
+    gen = torch.Generator().manual_seed(51 + w3)
+    nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w2, generator=gen), dim=1).to(DEV)
+    nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w3, generator=gen), dim=1).to(DEV)
+    B = sa.CorrBlockB200
+    old = B.mono_mode
+    try:
+        B.mono_mode = "otf"
+        otf = B.from_normals(nl, nr)
+        assert otf._packed is None and otf._otf
+        B.mono_mode = "packed"
+        pk = B.from_normals(nl, nr)
+        assert pk._packed is not None
+    finally:
+        B.mono_mode = old
+    stereo = B(torch.randn(b, h, w2, 1, w3, generator=gen).to(DEV))
+    x = torch.arange(w2, dtype=torch.float32).view(1, 1, 1, w2).expand(b, 1, h, w2) * (w3 / w2)
+    for kind, dx in (("left", -torch.rand(b, 1, h, w2, generator=gen) * (w3 / 3)), ("right", torch.rand(b, 1, h, w2, generator=gen) * 60),
+                     ("far", (torch.rand(b, 1, h, w2, generator=gen) - 0.5) * 4 * w3), ("int", -torch.randint(0, 9, (b, 1, h, w2), generator=gen).float())):
+        coords = torch.cat([x + dx, torch.zeros(b, 1, h, w2)], 1).to(DEV)
+        want = pk(coords)
+        assert torch.equal(otf(coords), want), kind
+        s1, m1 = B.lookup_pair(stereo, otf, coords)
+        s2, m2 = B.lookup_pair(stereo, pk, coords)
+        assert torch.equal(m1, want) and torch.equal(m2, want) and torch.equal(s1, s2), kind
+    # consumers that need the packed array get it on demand; the reference attributes still work
+    assert torch.equal(otf.fullcorr, pk.fullcorr)
+    w = (torch.randn(64, 36, 1, 1, generator=gen) / 6).to(DEV)
+    bias = torch.zeros(64, device=DEV)
+    fa, fb = sa.lookup_pair_convc1(stereo, otf, coords, w, bias)
+    ga, gb = sa.lookup_pair_convc1(stereo, pk, coords, w, bias)
+    assert torch.equal(fb, gb) and torch.equal(fa, ga)

@@ -542,7 +542,18 @@ def run_tiled(args):
     # while step k+1 computes; it is waited for when its buffer comes round again (step k+2) and before the
     # closing event of the timed region.  The weight plane sum(w) depends on the geometry only: rank 0 forms
     # it once (tiling.weight_sum) instead of reducing it every step.
-    acc_bufs = [torch.empty(args.images, H, W, device=dev) for _ in range(2)]
+    stitcher = None
+    if dist is not None and args.stitch == "peer":
+        # reduce + normalise + gather over NVLink peer memory in one kernel per rank (tiling.PeerStitcher) instead of
+        # an SM-resident NCCL reduce next to the persistent GEMM kernels; falls back to NCCL if symmetric memory
+        # cannot be set up on this box
+        try:
+            stitcher = tiling.PeerStitcher(args.images, H, W, tiling.weight_sum(H, W, work, device=dev), dev)
+        except Exception as e:  # pragma: no cover
+            if rank == 0:
+                print(f"[bench] peer stitch unavailable ({type(e).__name__}: {e}); using NCCL reduce", file=sys.stderr)
+            stitcher = None
+    acc_bufs = [torch.empty(args.images, H, W, device=dev) for _ in range(2)] if stitcher is None else None
     den = torch.clamp(tiling.weight_sum(H, W, work, device=dev), min=1e-4) if rank == 0 else None
     pending = [None, None]
     step_no = [0]
@@ -559,8 +570,11 @@ def run_tiled(args):
     def step():
         i = step_no[0] & 1
         step_no[0] += 1
-        finish(i)
-        accs = acc_bufs[i]
+        if stitcher is not None:
+            accs = stitcher.buffer(i)
+        else:
+            finish(i)
+            accs = acc_bufs[i]
         accs.zero_()
         for img, (y0, y1, x0, x1), mult in mine:
             pad = tiling.pad_to_32(y1 - y0, x1 - x0)
@@ -571,9 +585,15 @@ def run_tiled(args):
             if key not in weights:
                 weights[key] = tiling.blend_weight(key[0], key[1], device=dev) * float(mult)
             accs[img, y0:y1, x0:x1].addcmul_(full[0, 0], weights[key])
-        pending[i] = dist.reduce(accs, dst=0, op=dist.ReduceOp.SUM, async_op=True) if dist is not None else "local"
+        if stitcher is not None:
+            stitcher.reduce_to(i, 0)
+        else:
+            pending[i] = dist.reduce(accs, dst=0, op=dist.ReduceOp.SUM, async_op=True) if dist is not None else "local"
 
     def drain():
+        if stitcher is not None:
+            stitcher.drain()
+            return [stitcher.result()]
         outs = [finish(i) for i in range(2)]
         return outs
 
@@ -607,7 +627,9 @@ def run_tiled(args):
             "data": "synthetic", "config": {"workload": args.workload, "images_per_step": args.images, "tile_preset": args.tile_preset,
                                            "distinct_tiles_per_image": len(work), "tiles_this_rank": len(mine),
                                            "cuda_graph": bool(args.graph),
-                                           "parallelism": f"tiles sharded x{world}, one async reduce(sum) of [images,H,W] per step"},
+                                           "parallelism": (f"tiles sharded x{world}, stitch = reduce + normalise + gather over NVLink peer memory, one "
+                                                           f"kernel per rank (sa_peer_reduce), side stream") if stitcher is not None else
+                                                          f"tiles sharded x{world}, one async NCCL reduce(sum) of [images,H,W] per step"},
         }), flush=True)
     if dist is not None:
         dist.barrier()
@@ -695,6 +717,9 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + ["c4_middlebury_1984x2872_tiled"])
     ap.add_argument("--tile-preset", default="middlebury", help="reference tile preset for the tiled workload")
     ap.add_argument("--images", type=int, default=4, help="full-resolution pairs per step of the tiled workload")
+    ap.add_argument("--stitch", default="nccl", choices=["peer", "nccl"],
+                    help="tiled workload, N > 1: async NCCL reduce (default, measured faster) or reduce + normalise + gather over "
+                         "NVLink peer memory (tiling.PeerStitcher / sa_peer_reduce)")
     ap.add_argument("--variant", default="fused", choices=["fused", "protocol"],
                     help="fused: truncate= / mono_corr / lookup_pair entry points; protocol: the reference's exact call sequence")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"], help="stereo correlation kernel")

@@ -188,6 +188,14 @@ int sa_pyramid_backward(float* d0, const float* const* h_dlevels, const int* h_w
                         int num_levels, int64_t rows, const float* trunc_disp, const float* trunc_conf, double trunc_gain,
                         int w2_size, void* stream);
 
+/* ---------------------------------------------------------------- config 4: stitch over peer memory
+ * dst[i] = (sum_k h_srcs[k][i]) / den[i]  (den == NULL: plain sum), i < n, n % 4 == 0.
+ * h_srcs is a HOST array of n_src (<= 16) device pointers that may live on other GPUs of the node (NVLink peer
+ * access enabled, e.g. torch symmetric memory): every rank reduces its slice of the per-rank accumulators
+ * `sum disp * w` of the tile-sharded inference, normalises it by the weight plane and stores it into the
+ * gathering rank's output (mapreduce_v2/tile_wrapper.py:185,340-362) - reduce + normalise + gather in one pass. */
+int sa_peer_reduce(const float* const* h_srcs, int n_src, const float* den, float* dst, int64_t n, void* stream);
+
 /* ---------------------------------------------------------------- A5: truncation mask (standalone)
  * mask[b,h,w2,w3] = (1-c) + c * (sigmoid((w2 - d) - w3) * (1-g) + g); writes `out` = mask * vol
  * when vol != NULL, else the mask itself.  Replaces `truncate_corr_volume_v2`

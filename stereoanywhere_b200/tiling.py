@@ -191,3 +191,72 @@ def gather_batch(local: torch.Tensor, group=None) -> torch.Tensor:
     parts = [torch.empty_like(local) for _ in range(world)]
     dist.all_gather(parts, local.contiguous(), group=group)
     return torch.cat(parts, dim=0)
+
+
+class PeerStitcher:
+    """Stitch of a tile-sharded step over NVLink peer memory instead of an NCCL reduce (config 4).
+
+    Every rank accumulates `sum disp * w` for its tiles into a SYMMETRIC buffer (torch symmetric memory: the same
+    allocation is mapped into every process of the node).  `reduce_to(dst_rank)` then lets each rank sum its own
+    1/N slice of all N accumulators through peer loads, divide by the weight plane (geometry only, formed locally)
+    and store the slice into `dst_rank`'s output buffer: reduce + normalise + gather in ONE kernel per rank
+    (`sa_peer_reduce`), bracketed by two device-side barriers.  It runs on a side stream, double-buffered, so the
+    next step's tiles compute meanwhile - and unlike an SM-resident NCCL reduce it does not sit on SMs that the
+    persistent GEMM kernels of the next tile expect to own.
+    """
+
+    def __init__(self, images: int, height: int, width: int, den: torch.Tensor, device, group=None):
+        import ctypes as C
+
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+
+        from . import _lib
+
+        self._C, self._lib = C, _lib.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.n = images * height * width
+        assert self.n % 4 == 0
+        self.acc = [symm.empty(images, height, width, dtype=torch.float32, device=device) for _ in range(2)]
+        self.acc_h = [symm.rendezvous(t, self.group) for t in self.acc]
+        self.out = symm.empty(images, height, width, dtype=torch.float32, device=device)
+        self.out_h = symm.rendezvous(self.out, self.group)
+        self.den = den.to(device).float().clamp(min=1e-4).unsqueeze(0).expand(images, height, width).contiguous()
+        per = (self.n // 4 + self.world - 1) // self.world * 4
+        self.lo = min(self.n, self.rank * per)
+        self.hi = min(self.n, self.lo + per)
+        self.side = torch.cuda.Stream(device=device)
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        for e in self.free:
+            e.record(torch.cuda.current_stream(device))
+
+    def buffer(self, i: int) -> torch.Tensor:
+        """Accumulator of parity i; waits (on the current stream) until every rank has finished reading it."""
+        torch.cuda.current_stream().wait_event(self.free[i])
+        return self.acc[i]
+
+    def reduce_to(self, i: int, dst_rank: int = 0) -> None:
+        main = torch.cuda.current_stream()
+        self.ready[i].record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ready[i])
+            self.acc_h[i].barrier(channel=0)          # every rank's accumulator i is complete
+            if self.hi > self.lo:
+                C = self._C
+                ptrs = (C.c_void_p * self.world)(*[int(p) + 4 * self.lo for p in self.acc_h[i].buffer_ptrs])
+                dst = int(self.out_h.buffer_ptrs[dst_rank]) + 4 * self.lo
+                rc = self._lib.sa_peer_reduce(ptrs, self.world, self.den.data_ptr() + 4 * self.lo, dst, self.hi - self.lo,
+                                              self.side.cuda_stream)
+                if rc != 0:
+                    raise RuntimeError("sa_peer_reduce: " + self._lib.sa_last_error().decode())
+            self.out_h.barrier(channel=1)             # all slices stored, all peer reads of accumulator i done
+            self.free[i].record(self.side)
+
+    def result(self) -> torch.Tensor:
+        """The stitched images on the gathering rank (valid after the side stream has been waited for)."""
+        return self.out
+
+    def drain(self) -> None:
+        torch.cuda.current_stream().wait_stream(self.side)

@@ -85,3 +85,29 @@ def test_streams_are_respected(lib):
         out = sa.CorrBlockB200(v2)(coords)
     side.synchronize()
     assert torch.allclose(out, 2.0 * ref, atol=1e-6)
+
+
+def test_peer_reduce_local_pointers():
+    """sa_peer_reduce on one GPU (the pointers of a multi-GPU run are NVLink peer pointers of the same kind)."""
+    import ctypes as C
+
+    import torch
+
+    from stereoanywhere_b200 import _lib
+
+    lib = _lib.load()
+    gen = torch.Generator(device="cuda:0").manual_seed(3)
+    srcs = [torch.randn(4096, device="cuda:0", generator=gen) for _ in range(5)]
+    den = torch.rand(4096, device="cuda:0", generator=gen) + 0.5
+    dst = torch.empty(4096, device="cuda:0")
+    ptrs = (C.c_void_p * 5)(*[t.data_ptr() for t in srcs])
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.sa_peer_reduce(ptrs, 5, den.data_ptr(), dst.data_ptr(), 4096, st) == 0
+    want = srcs[0].clone()
+    for t in srcs[1:]:
+        want += t
+    assert torch.equal(dst, want / den)
+    assert lib.sa_peer_reduce(ptrs, 5, None, dst.data_ptr(), 4096, st) == 0
+    assert torch.equal(dst, want)
+    assert lib.sa_peer_reduce(ptrs, 17, None, dst.data_ptr(), 4096, st) == -1   # more than 16 sources
+    assert lib.sa_peer_reduce(ptrs, 5, None, dst.data_ptr(), 4098, st) == -2    # n % 4

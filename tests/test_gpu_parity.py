@@ -703,3 +703,33 @@ def test_mono_lookup_on_the_fly_is_bit_identical(sa, shape):
     fa, fb = sa.lookup_pair_convc1(stereo, otf, coords, w, bias)
     ga, gb = sa.lookup_pair_convc1(stereo, pk, coords, w, bias)
     assert torch.equal(fb, gb) and torch.equal(fa, ga)
+
+
+def test_more_than_2_31_packed_floats(sa):
+    """SceneFlow size at batch 64 on one GPU (BASELINE config 3 before sharding): each packed array holds 2.6e9
+    floats - past int32.  Every sample of the big batch must equal the same sample run alone (64-bit indexing in
+    the packers, the TMA maps and the lookup)."""
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs ~35 GB of device memory")
+    b, c, h, w = 64, 64, 136, 240
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    fl = torch.randn(b, c, h, w, device=DEV, generator=gen)
+    fr = torch.randn(b, c, h, w, device=DEV, generator=gen)
+    nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w, device=DEV, generator=gen), dim=1)
+    nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w, device=DEV, generator=gen), dim=1)
+    td = torch.rand(b, 1, h, w, device=DEV, generator=gen) * (w / 4)
+    tc = torch.rand(b, 1, h, w, device=DEV, generator=gen)
+    x = torch.arange(w, device=DEV, dtype=torch.float32).view(1, 1, 1, w).expand(b, 1, h, w)
+    coords = torch.cat([x - torch.rand(b, 1, h, w, device=DEV, generator=gen) * (w / 4), torch.zeros(b, 1, h, w, device=DEV)], 1)
+    B = sa.CorrBlockB200
+    fs = B.from_features(fl, fr, truncate=(td, tc, 0.9))
+    fm = B.from_normals(nl, nr)
+    assert fs._packed.numel() > 2 ** 31
+    s_all, m_all = B.lookup_pair(fs, fm, coords)
+    del fs, fm
+    for i in (0, 31, 63):
+        sl = slice(i, i + 1)
+        f1 = B.from_features(fl[sl].contiguous(), fr[sl].contiguous(), truncate=(td[sl].contiguous(), tc[sl].contiguous(), 0.9))
+        m1 = B.from_normals(nl[sl].contiguous(), nr[sl].contiguous())
+        s1, mm1 = B.lookup_pair(f1, m1, coords[sl].contiguous())
+        assert torch.equal(s_all[sl], s1) and torch.equal(m_all[sl], mm1), i

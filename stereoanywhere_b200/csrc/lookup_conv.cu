@@ -31,7 +31,7 @@ struct LcArgs {
   const float* weight;  // [64][36]
   const float* bias;    // [64]
   long long coords_bstride;
-  int HW, nblk;
+  int HW, nblk, B;
 };
 
 __device__ __forceinline__ void lc_cp_async16(void* smem_dst, const void* gsrc) {
@@ -70,23 +70,6 @@ __global__ void __launch_bounds__(2 * kLcTile) lookup_conv_kernel(const LcArgs a
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int b = blockIdx.y;
-  const int hw0 = blockIdx.x * TILE;
-  const int npx = min(TILE, a.HW - hw0);
-  const long long row0 = (long long)b * a.HW + hw0;
-
-  if (tid < TILE) {
-    float x = 0.f;
-    int blk = -1;
-    if (tid < npx) {
-      x = __ldg(a.coords + (long long)b * a.coords_bstride + hw0 + tid);
-      const float fl = fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
-      const int q = ((int)fl >> 3) + 5;  // blocks start at q = -5 (csrc/packed.cu)
-      if (q >= 0 && q < a.nblk) blk = q;
-    }
-    s_x[tid] = x;
-    s_blk[tid] = blk;
-  }
   // weights -> K-major 8x(16 B) core matrices, rounded to tf32; channels 36..39 are zero padding
   if ((reinterpret_cast<uintptr_t>(a.weight) & 15) == 0) {
     // one float4 (four consecutive k of one output channel) per step: 128-bit load, 4 x cvt, 128-bit store
@@ -120,6 +103,31 @@ __global__ void __launch_bounds__(2 * kLcTile) lookup_conv_kernel(const LcArgs a
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+
+  // persistent: the weights, the TMEM allocation and the barrier are set up once per CTA; tiles of 128 pixels
+  // are taken round-robin
+  const int tiles_x = (a.HW + TILE - 1) / TILE;
+  const long long ntiles = (long long)tiles_x * a.B;
+  uint32_t phase = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b = (int)(tile / tiles_x);
+    const int hw0 = (int)(tile - (long long)b * tiles_x) * TILE;
+  const int npx = min(TILE, a.HW - hw0);
+  const long long row0 = (long long)b * a.HW + hw0;
+
+  if (tid < TILE) {
+    float x = 0.f;
+    int blk = -1;
+    if (tid < npx) {
+      x = __ldg(a.coords + (long long)b * a.coords_bstride + hw0 + tid);
+      const float fl = fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
+      const int q = ((int)fl >> 3) + 5;  // blocks start at q = -5 (csrc/packed.cu)
+      if (q >= 0 && q < a.nblk) blk = q;
+    }
+    s_x[tid] = x;
+    s_blk[tid] = blk;
+  }
+  __syncthreads();
 
   // ---- stage one packed line per (pixel, volume), chunk c of pixel p at chunk c ^ (p & 7)
   float* stage = reinterpret_cast<float*>(sA);
@@ -238,7 +246,8 @@ __global__ void __launch_bounds__(2 * kLcTile) lookup_conv_kernel(const LcArgs a
     }
     __syncwarp();
   }
-  mbar_wait(bar, 0);
+  mbar_wait(bar, phase);
+  phase ^= 1u;
   tc_fence_after();
 
   // ---- epilogue: warp w reads TMEM lanes 32*(w%4).. (its pixels), columns of its volume (w/4)
@@ -268,7 +277,9 @@ __global__ void __launch_bounds__(2 * kLcTile) lookup_conv_kernel(const LcArgs a
     }
   }
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();  // the next tile rewrites the shared-memory operands and the accumulators
+  tc_fence_after();
+  }
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
 }
 
@@ -291,10 +302,13 @@ extern "C" int sa_lookup_packed_conv(const float* packed_a, const float* packed_
   a.weight = weight; a.bias = bias;
   a.HW = H * W;
   a.nblk = W3 / 8 + 9;
+  a.B = B;
   const size_t smem = 1024 + 2 * kLcABytes + kLcBBytes + (kLcN + 2 * kLcTile) * sizeof(float) + 32;
   cudaError_t e = cudaFuncSetAttribute(lookup_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) SA_FAIL((int)e, "sa_lookup_packed_conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  dim3 grid((a.HW + kLcTile - 1) / kLcTile, B);
+  const long long ntiles = (long long)((a.HW + kLcTile - 1) / kLcTile) * B;
+  const long long cap = (long long)num_sms() * 4;  // 4 CTAs per SM fit (shared memory, 128 TMEM columns each)
+  const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
   lookup_conv_kernel<<<grid, 2 * kLcTile, smem, (cudaStream_t)stream>>>(a);
   return finish_launch("sa_lookup_packed_conv");
 }

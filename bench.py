@@ -241,6 +241,7 @@ def run_gpu(args):
     sa.CorrBlockB200.precision = args.precision
     sa.CorrBlockB200.mono_mode = args.mono
     otf = args.variant == "fused" and args.mono == "otf"
+    factored = args.variant == "fused" and args.mono == "factored"
     b, c, h, w = WORKLOADS[args.workload]
     host, d = make_inputs(b, c, h, w, dev, seed=rank, pinned=True)
     torch.cuda.synchronize()
@@ -420,8 +421,9 @@ def run_gpu(args):
         p = b * h * w
         # algorithmic bytes per pixel and launch: coords 4 + 160 per volume of windows + 144 per volume of
         # outputs.  With the mono volume computed on the fly its 160 B of windows are not memory traffic any more.
-        alg_px = (452 if otf else 612) if args.variant == "fused" else 308
-        real_px = (416 if otf else 544)
+        # Factored mono volume: its windows come out of the L2-resident packed right normals; the left normal is read.
+        alg_px = (452 if otf else 464 if factored else 612) if args.variant == "fused" else 308
+        real_px = (416 if otf else 432 if factored else 544)
         alg = alg_px * p
         achieved = alg / (lk_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "lookup_packed_kernel" + ("<NV=2>" if args.variant == "fused" else "<NV=1>"),
@@ -435,6 +437,7 @@ def run_gpu(args):
             st_us = breakdown[0] * 1e3
             mo_us = breakdown[1] * 1e3 if breakdown[1] is not None else None
             packed = p * (w // 8 + 9) * 128
+            mono_bytes = 3 * b * h * (w // 8 + 9) * 128 + 3 * b * h * w * 4 if factored else packed
             tf32_peak = tensor_peak_tf32()
             tflops = 2.0 * p * w * c / (st_us * 1e-6) / 1e12
             kernels = {
@@ -443,8 +446,10 @@ def run_gpu(args):
                                    "tflops": round(tflops, 1), "tensor_peak_tf32": tf32_peak,
                                    "tensor_frac": round(tflops / tf32_peak, 4),
                                    "note": "HBM-bound by the packed write; the tensor pipe is reported, not targeted"},
-                "pack_normals": ({"us": round(mo_us, 1), "hbm_gbs": round(packed / mo_us / 1e3, 1),
-                                  "hbm_frac": round(packed / mo_us / 1e3 / peak, 4)} if mo_us is not None else
+                "pack_normals": ({"us": round(mo_us, 1), "hbm_gbs": round(mono_bytes / mo_us / 1e3, 1),
+                                  "hbm_frac": round(mono_bytes / mo_us / 1e3 / peak, 4),
+                                  **({"note": "factored: only the right normal map's rows are packed (launch-bound)"} if factored else {})}
+                                 if mo_us is not None else
                                  "not launched: the mono lookups are computed from the normal maps inside the lookup kernel"),
                 "lookup_packed2": {"us": round(lk_launch_ms * 1e3, 2), "launches": n_lk_launch,
                                    "real_bytes_per_pixel": real_px,
@@ -460,7 +465,9 @@ def run_gpu(args):
             "config": {"workload": args.workload, "pairs_per_gpu": b, "C": c, "H4": h, "W4": w, "iters": ITERS,
                        "levels": LEVELS, "radius": RADIUS, "variant": args.variant, "cuda_graph": bool(args.graph),
                        "mono": ("on the fly: lookups computed from the normal maps inside the lookup kernel, bit-identical to "
-                                "the packed pyramid (no mono volume / pyramid in memory)") if otf else "packed pyramid",
+                                "the packed pyramid (no mono volume / pyramid in memory)") if otf else
+                               ("factored: packed pyramid of the right normal map's rows (rank-3 volume, linear pyramid); "
+                                "the lookup combines three lines with the pixel's left normal") if factored else "packed pyramid",
                        "l2": "inputs+volumes (>1 GB/step) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"batch-sharded x{world}, async all_gather of quarter-res disparity per step"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -648,6 +655,9 @@ TRAFFIC_BYTES = {
     # profiles/r1/lookup_tile64_pack_normals_ncu_summary.txt: 60.46 MB read + 13.9 MB written while the kernel runs
     # (the other ~55 MB of its 69 MB output are still dirty in L2 at kernel end and reach HBM later)
     ("c2_kitti_375x1242_b8", "fused", "packed"): 74_360_000,
+    # profiles/r1/lookup_factored_ncu_summary.txt: 46.2 MB read (30.7 MB of stereo lines, the left normals, the coords,
+    # first touches of the packed right normals) + 12.5-13.9 MB written while the kernel runs
+    ("c2_kitti_375x1242_b8", "fused", "factored"): 59_440_000,
 }
 
 
@@ -729,8 +739,9 @@ def main():
     ap.add_argument("--variant", default="fused", choices=["fused", "protocol"],
                     help="fused: truncate= / mono_corr / lookup_pair entry points; protocol: the reference's exact call sequence")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"], help="stereo correlation kernel")
-    ap.add_argument("--mono", default="packed", choices=["otf", "packed"],
-                    help="mono block of the fused variant: lookups computed on the fly from the normals, or the packed pyramid")
+    ap.add_argument("--mono", default="factored", choices=["otf", "packed", "factored"],
+                    help="mono block of the fused variant: factored (packed right normals, combined inside the lookup), "
+                         "the packed pyramid of the volume, or lookups computed on the fly from the normals")
     ap.add_argument("--graph", type=int, default=1, help="replay the step from a CUDA graph in the device-resident run")
     ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

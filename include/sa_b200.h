@@ -135,6 +135,19 @@ int sa_lookup_packed_normals(const float* packed_a, const float* normals_l, cons
                              float post_scale, int W3, const float* coords, int64_t coords_bstride, float* out_a,
                              float* out_mono, int B, int H, int W, void* stream);
 
+/* Lookup with the MONO volume in FACTORED form.  The volume of stereoanywhere.py:136 has rank 3 (V = g * nL^T nR /
+ * sqrt 3) and both the avg-pool pyramid (corr.py:88-91) and the packed layout are linear in it, so the packed line
+ * of pixel (b,h,w2) is the combination, with nL[b,:,h,w2] as coefficients, of the packed lines of the three
+ * right-normal rows.  packed_normals_r = sa_pack_pyramid(normals_r viewed as B*3*H rows of W3) - 14 MB at KITTI
+ * size, L2-resident, written in ~10 us - replaces the 1.47 GB packed mono volume.  Differences from
+ * sa_pack_pyramid_normals + sa_lookup_packed are fp32 rounding only (post_scale / divisor is applied to the
+ * coefficients; stored border entries of levels 1..3 are pooled before the contraction): |delta| <= 1e-6 for unit
+ * normals.  packed_a / out_a: an
+ * ordinary packed volume looked up in the same launch (both NULL: mono only).  normals_l is [B,3,H,W]. */
+int sa_lookup_packed_factored(const float* packed_a, const float* packed_normals_r, const float* normals_l,
+                              float divisor, float post_scale, int W3, const float* coords, int64_t coords_bstride,
+                              float* out_a, float* out_mono, int B, int H, int W, void* stream);
+
 /* ---------------------------------------------------------------- A1 + A5 + A3 fused (tensor cores -> packed pyramid)
  * packed = sa_pack_pyramid(T * sa_corr_tf32(L, R)) in ONE kernel: the truncation product and the avg-pooled
  * pyramid are formed in the GEMM epilogue (TMEM -> registers -> packed lines -> TMA store); the fp32 volume

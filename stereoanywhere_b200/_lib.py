@@ -57,6 +57,8 @@ def _declare(lib):
     lib.sa_pyramid_backward.argtypes = [vp, vp, vp, vp, i, i64, vp, vp, d, i, vp]
     lib.sa_lookup_packed_normals.restype = i
     lib.sa_lookup_packed_normals.argtypes = [vp, vp, vp, f, f, i, vp, i64, vp, vp, i, i, i, vp]
+    lib.sa_lookup_packed_factored.restype = i
+    lib.sa_lookup_packed_factored.argtypes = [vp, vp, vp, f, f, i, vp, i64, vp, vp, i, i, i, vp]
     lib.sa_peer_reduce.restype = i
     lib.sa_peer_reduce.argtypes = [vp, i, vp, vp, i64, vp]
     lib.sa_lookup_packed_conv.restype = i
@@ -71,7 +73,7 @@ def _declare(lib):
 
 EXPORTS = [
     "sa_abi_version", "sa_last_error", "sa_corr_fp32", "sa_corr_tf32", "sa_pyramid", "sa_lookup", "sa_lookup2",
-    "sa_truncate", "sa_masked_volume", "sa_corrupt", "sa_packed_row_floats", "sa_pack_pyramid", "sa_pack_pyramid_normals", "sa_lookup_packed", "sa_lookup_packed_conv", "sa_corr_pack_tf32", "sa_peer_reduce", "sa_lookup_packed_normals", "sa_lookup_backward", "sa_pyramid_backward", "sa_volume_softargmax", "sa_volume_entropy_conf",
+    "sa_truncate", "sa_masked_volume", "sa_corrupt", "sa_packed_row_floats", "sa_pack_pyramid", "sa_pack_pyramid_normals", "sa_lookup_packed", "sa_lookup_packed_conv", "sa_corr_pack_tf32", "sa_peer_reduce", "sa_lookup_packed_normals", "sa_lookup_packed_factored", "sa_lookup_backward", "sa_pyramid_backward", "sa_volume_softargmax", "sa_volume_entropy_conf",
 ]
 
 
@@ -80,12 +82,14 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
+    # Bring the .so up to date with csrc/ first (a no-op when the stamp matches; dlopen caches by path, so a stale
+    # library cannot be replaced once it has been opened).  Without nvcc an existing, current .so is used as it is.
+    from . import build as _build
 
-        try:
-            _build.build()
-        except Exception as e:  # no nvcc, compile error ...
+    try:
+        _build.build()
+    except Exception as e:  # no nvcc, compile error ...
+        if not os.path.exists(LIB_PATH):
             raise SaError(
                 f"stereoanywhere_b200: CUDA library {LIB_PATH} is missing and could not be built ({e}). "
                 "There is no CPU fallback; run `python -m stereoanywhere_b200.build`."
@@ -93,15 +97,9 @@ def load():
     try:
         lib = C.CDLL(LIB_PATH)
         _declare(lib)
-    except (OSError, AttributeError) as stale:  # .so older than this binding: rebuild once
-        from . import build as _build
-
-        try:
-            _build.build(force=True)
-        except Exception as e:
-            raise SaError(f"stereoanywhere_b200: {LIB_PATH} is stale ({stale}) and could not be rebuilt ({e})") from e
-        lib = C.CDLL(LIB_PATH)
-        _declare(lib)
+    except (OSError, AttributeError) as stale:
+        raise SaError(f"stereoanywhere_b200: {LIB_PATH} does not match this binding ({stale}); "
+                      "run `python -m stereoanywhere_b200.build --force`") from stale
     if lib.sa_abi_version() != 1:
         raise SaError("stereoanywhere_b200: ABI version mismatch between _lib.py and libsa_b200.so")
     _lib = lib

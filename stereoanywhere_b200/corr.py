@@ -162,7 +162,8 @@ class CorrBlockB200:
                      gain: float = 1.73) -> "CorrBlockB200":
         """The mono block of stereoanywhere.py:136 + :257-259 in one pass: the lookup structure of
         `gain * corr(nL, nR)` is written straight from the normal maps; the volume itself is only formed
-        if `fullcorr` / `corr_pyramid` are read.  Same values as `cls(cls.mono_corr(nL, nR))`."""
+        if `fullcorr` / `corr_pyramid` are read.  Same values as `cls(cls.mono_corr(nL, nR))` - bit for bit with
+        `mono_mode` "packed" / "otf", to fp32 rounding with the default "factored" (see `mono_mode`)."""
         b, c, h, w2 = normals2.shape
         w3 = normals3.shape[3]
         if _needs_grad(normals2, normals3) or not (cls.layout == "packed" and ops.packable(num_levels, radius, w3, [0, 0])):
@@ -178,22 +179,30 @@ class CorrBlockB200:
         self._dlevels, self._handle = None, None
         self._packed = None
         self._otf = cls.mono_mode == "otf"  # on-the-fly lookups (see mono_mode)
-        if not self._otf:
+        self._packed_nr = None
+        if cls.mono_mode == "factored":     # packed pyramid of the right normal map's B*3*H rows (see mono_mode)
+            self._packed_nr = _OPS.pack_pyramid(self._normals[1].contiguous().view(b * 3 * h, w3), None, None, 0.0)
+        elif not self._otf:
             self._packed = _OPS.pack_pyramid_normals(self._normals[0], self._normals[1], float(gain))
         return self
 
-    #: how a block built by `from_normals` serves its lookups: "packed" (default) writes the packed pyramid once
-    #: (241 us at KITTI size, batch 8) and every lookup reads one line; "otf" keeps only the normal maps and
-    #: computes every lookup inside the lookup kernel - bit-identical, no 1.5 GB packed array, but 44.6 us instead
-    #: of 23.3 us per dual lookup (80 three-channel dot products per pixel), i.e. a memory-saving mode, not a
-    #: faster one for 32 iterations.  SA_B200_MONO overrides the default.
-    mono_mode = os.environ.get("SA_B200_MONO", "packed")
+    #: how a block built by `from_normals` serves its lookups.
+    #: "factored" (default) uses the volume's rank: V = gain * nL^T nR / sqrt 3, and the pyramid and the packed
+    #: layout are linear in V, so only the right normal map's B*3*H rows are packed (14 MB instead of 1.47 GB at
+    #: KITTI size, batch 8; L2-resident, 10 us) and the lookup kernel combines three of their lines with the pixel's
+    #: left normal while staging: no mono pack pass (241 us) and half the lookup's DRAM reads; within fp32 rounding
+    #: (<= 1e-6 abs) of the packed mode.  "packed" writes the packed pyramid of the volume itself, bit-identical to
+    #: `cls(cls.mono_corr(nL, nR))`.  "otf" keeps only the normal maps and forms 80 level-0 values per pixel inside
+    #: the lookup kernel - bit-identical to "packed" too, but 44.6 us instead of 23.3 us per dual lookup.
+    #: SA_B200_MONO overrides the default.
+    mono_mode = os.environ.get("SA_B200_MONO", "factored")
 
     def _ensure_packed(self) -> torch.Tensor:
-        """The packed pyramid of this block (built on demand for on-the-fly mono blocks)."""
-        if self._packed is None and getattr(self, "_otf", False):
+        """The packed pyramid of this block (built on demand for on-the-fly / factored mono blocks)."""
+        if self._packed is None and (getattr(self, "_otf", False) or getattr(self, "_packed_nr", None) is not None):
             self._packed = _OPS.pack_pyramid_normals(self._normals[0], self._normals[1], self._normals[2])
             self._otf = False
+            self._packed_nr = None
         return self._packed
 
     @classmethod
@@ -261,6 +270,8 @@ class CorrBlockB200:
     def _lookup_nograd(self, coords: torch.Tensor) -> torch.Tensor:
         if getattr(self, "_otf", False):
             return _OPS.lookup_normals(self._normals[0], self._normals[1], self._normals[2], coords)
+        if getattr(self, "_packed_nr", None) is not None:
+            return _OPS.lookup_factored(self._packed_nr, self._normals[0], self._normals[2], coords)
         if self._packed is not None:
             return _OPS.lookup_packed(self._packed, self._shape[3], coords)
         return _OPS.lookup(self._levels, self._widths, coords, self.radius, self.pad[0], self.pad[1])
@@ -310,15 +321,20 @@ class CorrBlockB200:
         _no_grad_check(coords)
         if torch.is_grad_enabled() and (block_a._handle is not None or block_b._handle is not None):
             return block_a(coords), block_b(coords)  # training: each lookup is its own autograd node
-        otf_b = getattr(block_b, "_otf", False)
+        fact_b = getattr(block_b, "_packed_nr", None) is not None
+        otf_b = getattr(block_b, "_otf", False) or fact_b  # block_b holds no packed volume of its own
         if (block_a.radius != block_b.radius or block_a._widths != block_b._widths
                 or block_a.pad != [0, 0] or block_b.pad != [0, 0] or getattr(block_a, "_otf", False)
+                or getattr(block_a, "_packed_nr", None) is not None
                 or (block_a._packed is None) != (block_b._packed is None and not otf_b)):
             return block_a(coords), block_b(coords)
         dt = coords.dtype
         if dt != torch.float32:
             coords = coords.float()
-        if block_a._packed is not None and getattr(block_b, "_otf", False):
+        if block_a._packed is not None and fact_b:
+            oa, ob = _OPS.lookup_packed_factored2(block_a._packed, block_b._packed_nr, block_b._normals[0],
+                                                  block_b._normals[2], coords)
+        elif block_a._packed is not None and getattr(block_b, "_otf", False):
             oa, ob = _OPS.lookup_packed_normals2(block_a._packed, block_b._normals[0], block_b._normals[1],
                                                  block_b._normals[2], coords)
         elif block_a._packed is not None:

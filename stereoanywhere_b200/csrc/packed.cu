@@ -211,6 +211,8 @@ struct PLookupArgs {
   const float* nr;
   int H, Wimg;
   float divisor, inv_divisor, post_scale;
+  // factored mono volume (FV >= 0): packed[FV] holds the packed pyramid of the RIGHT NORMAL MAP's rows,
+  // [(b*3 + c)*H + h][nblk][32]; nl / H / Wimg / divisor / inv_divisor / post_scale as above
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -231,8 +233,18 @@ __device__ __forceinline__ void shift_if(float (&v)[N], bool on, int by, int kee
 // FMAs, the division and the 1.73 scale in pack_kernel<normals>'s order - and pools them with the pyramid's own
 // 0.5 (a + b): exactly the 17 + 13 + 11 + 10 window entries the packed path holds after its derivation step, bit
 // for bit.  ~900 instructions per pixel instead of a 128-byte line read, and no mono pack pass at all.
-template <int NV, int TILE, int OTF>
+//
+// FV = index of a volume served in FACTORED form, or -1.  The mono volume has rank 3 and both the pyramid and the
+// packed layout are linear in the volume, so the packed line of pixel (b,h,w2) is the combination, with the three
+// left normals as coefficients, of the packed lines of the three right-normal rows (b,c,h) - a 14 MB array at
+// KITTI size that stays in L2, instead of the 1.47 GB packed mono volume.  The staging lanes load the three
+// 16-byte chunks, combine them with the pixel's left normal pre-multiplied by post_scale / divisor (one FMUL and
+// two FFMA per entry) and store the chunk; everything after staging is the packed path unchanged.  Differences
+// from the packed mono volume are fp32 rounding only (the scale is applied to the coefficients, and the 15 stored
+// border entries of levels 1..3 are pooled before the contraction instead of after it): <= 4e-7 for unit normals.
+template <int NV, int TILE, int OTF, int FV>
 __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupArgs a) {
+  static_assert(OTF < 0 || FV < 0, "one special mono form at a time");
   constexpr int THREADS = NV * TILE;
   constexpr int NC = 36;
   constexpr int SP = TILE + 4;
@@ -243,6 +255,8 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
   float* buf = smem;                                        // staging lines, later the output tile
   float* s_x = smem + BUF_FLOATS;                           // [TILE] x coordinate
   int* s_blk = reinterpret_cast<int*>(s_x + TILE);          // [TILE] block index or -1
+  // FV >= 0: per pixel {k n0, k n1, k n2, float offset of line (h, blk) inside a channel of the batch's rows}
+  float4* s_n = reinterpret_cast<float4*>(s_x + 2 * TILE);
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
@@ -253,21 +267,34 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
   if (tid < TILE) {
     float x = 0.f;
     int blk = -1;
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f;
     if (tid < npx) {
       x = __ldg(a.coords + (long long)b * a.coords_bstride + hw0 + tid);
+      if (FV >= 0) {  // issued together with the coordinate load: they do not depend on it
+        const long long plane = (long long)a.H * a.Wimg;
+        const float* nlp = a.nl + (long long)b * 3 * plane + hw0 + tid;  // h * Wimg + w2 == hw
+        n0 = __ldg(nlp); n1 = __ldg(nlp + plane); n2 = __ldg(nlp + 2 * plane);
+      }
       const float fl = fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
       const int q = ((int)fl >> 3) - kQMin;
       if (q >= 0 && q < a.nblk) blk = q;
     }
     s_x[tid] = x;
     s_blk[tid] = blk;
+    if (FV >= 0) {
+      // a pixel without a line (blk < 0) reads line 0 with zero coefficients: no branch in the staging loop
+      const float k = blk >= 0 ? a.post_scale * a.inv_divisor : 0.f;
+      const int off = blk >= 0 ? (((hw0 + tid) / a.Wimg) * a.nblk + blk) * 32 : 0;
+      s_n[tid] = make_float4(n0 * k, n1 * k, n2 * k, __int_as_float(off));
+    }
   }
   __syncthreads();
 
   // ---- stage one line per (pixel, volume): 8 lanes x 16 B, chunk c of pixel p lands at chunk c ^ (p & 7).
   // Thread tid copies chunk ch = tid & 7 of the units (tid >> 3) + n * THREADS/8, n < 8: the volume of a unit is
   // a compile-time function of n and its pixel one of 8/NV values, so the 64-bit line addresses are formed
-  // 8/NV times per thread and shared by the volumes.
+  // 8/NV times per thread and shared by the volumes.  (Forming them once per pixel in the prologue and passing
+  // them through shared memory saves 30 instructions per thread and changes nothing: 23.25 us - latency-bound.)
   {
     constexpr int UPS = THREADS / 8;   // units per step
     constexpr int SPV = 8 / NV;        // steps per volume
@@ -282,7 +309,7 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       const int v = n / SPV, m = n % SPV;  // compile-time
-      if (v == OTF) continue;
+      if (v == OTF || v == FV) continue;
       const int pm = u0 + m * UPS;
       float* dst = buf + (v * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2);
       if (goff[m] >= 0)
@@ -292,6 +319,31 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+  if (FV >= 0) {
+    // the factored volume's chunks while the copies above are in flight: all loads first, then the arithmetic
+    constexpr int UPS = THREADS / 8, SPV = 8 / NV;
+    const int ch = tid & 7, u0 = tid >> 3;
+    const int cplane = a.H * a.nblk * 32;  // floats between the channels of one (b, h)
+    const float* rp = a.packed[FV >= 0 ? FV : 0] + (long long)b * 3 * cplane + ch * 4;
+    float4 r[SPV][3], n[SPV];
+#pragma unroll
+    for (int m = 0; m < SPV; ++m) {
+      n[m] = s_n[u0 + m * UPS];
+      const int off = __float_as_int(n[m].w);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) r[m][c] = __ldg(reinterpret_cast<const float4*>(rp + (off + c * cplane)));
+    }
+#pragma unroll
+    for (int m = 0; m < SPV; ++m) {
+      const int pm = u0 + m * UPS;
+      float4 o;
+      o.x = fmaf(n[m].z, r[m][2].x, fmaf(n[m].y, r[m][1].x, n[m].x * r[m][0].x));
+      o.y = fmaf(n[m].z, r[m][2].y, fmaf(n[m].y, r[m][1].y, n[m].x * r[m][0].y));
+      o.z = fmaf(n[m].z, r[m][2].z, fmaf(n[m].y, r[m][1].z, n[m].x * r[m][0].z));
+      o.w = fmaf(n[m].z, r[m][2].w, fmaf(n[m].y, r[m][1].w, n[m].x * r[m][0].w));
+      *reinterpret_cast<float4*>(buf + ((FV >= 0 ? FV : 0) * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2)) = o;
+    }
+  }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
@@ -461,12 +513,12 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
   }
 }
 
-template <int NV, int TILE, int OTF>
+template <int NV, int TILE, int OTF, int FV>
 static int launch_packed_t(const PLookupArgs& a, int B, cudaStream_t st) {
   constexpr int NC = 36, SP = TILE + 4;
   constexpr int buf_floats = (NV * TILE * 32 > NV * NC * SP) ? NV * TILE * 32 : NV * NC * SP;
-  const size_t smem = (size_t)(buf_floats + 2 * TILE) * sizeof(float);
-  auto kern = lookup_packed_kernel<NV, TILE, OTF>;
+  const size_t smem = (size_t)(buf_floats + (FV >= 0 ? 6 : 2) * TILE) * sizeof(float)  /* s_x, s_blk [, float4 s_n] */;
+  auto kern = lookup_packed_kernel<NV, TILE, OTF, FV>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) SA_FAIL((int)e, "sa_lookup_packed: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -476,14 +528,15 @@ static int launch_packed_t(const PLookupArgs& a, int B, cudaStream_t st) {
   return finish_launch("sa_lookup_packed");
 }
 
-template <int NV, int OTF>
+template <int NV, int OTF, int FV = -1>
 static int launch_packed(const PLookupArgs& a, int B, cudaStream_t st) {
-  static const int tile = getenv("SA_B200_LOOKUP_TILE") ? atoi(getenv("SA_B200_LOOKUP_TILE")) : 64;
+  // (factored mono volume: 32 - 23.5 us against 24.4 at 64 and 27.3 at 128; its staging is latency-bound)
+  static const int tile = getenv("SA_B200_LOOKUP_TILE") ? atoi(getenv("SA_B200_LOOKUP_TILE")) : (FV >= 0 ? 32 : 64);
   // pixels per CTA: 64 measured best at c2 (23.2 us per dual lookup; 128: 24.2, 32: 23.5) - smaller CTAs
   // shorten the tail of the last wave and raise the number of lines in flight per SM
-  if (tile == 32) return launch_packed_t<NV, 32, OTF>(a, B, st);
-  if (tile == 128) return launch_packed_t<NV, 128, OTF>(a, B, st);
-  return launch_packed_t<NV, 64, OTF>(a, B, st);
+  if (tile == 32) return launch_packed_t<NV, 32, OTF, FV>(a, B, st);
+  if (tile == 128) return launch_packed_t<NV, 128, OTF, FV>(a, B, st);
+  return launch_packed_t<NV, 64, OTF, FV>(a, B, st);
 }
 
 }  // namespace sa
@@ -582,4 +635,30 @@ extern "C" int sa_lookup_packed_normals(const float* packed_a, const float* norm
   }
   a.out[0] = out_mono;
   return launch_packed<1, 0>(a, B, (cudaStream_t)stream);
+}
+
+extern "C" int sa_lookup_packed_factored(const float* packed_a, const float* packed_normals_r, const float* normals_l,
+                                         float divisor, float post_scale, int W3, const float* coords,
+                                         int64_t coords_bstride, float* out_a, float* out_mono, int B, int H, int W,
+                                         void* stream) {
+  using namespace sa;
+  SA_REQUIRE(packed_normals_r && normals_l && coords && out_mono, SA_E_INVALID, "sa_lookup_packed_factored: null pointer");
+  SA_REQUIRE((packed_a == nullptr) == (out_a == nullptr), SA_E_INVALID, "sa_lookup_packed_factored: packed_a / out_a must come together");
+  SA_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 31) && divisor != 0.f, SA_E_INVALID,
+             "sa_lookup_packed_factored: bad sizes");
+  SA_REQUIRE(W3 >= 8 && W3 % 8 == 0, SA_E_UNSUPPORTED, "sa_lookup_packed_factored: W3 must be a multiple of 8");
+  SA_REQUIRE(aligned16(packed_normals_r) && aligned16(out_mono) && (!packed_a || (aligned16(packed_a) && aligned16(out_a))),
+             SA_E_ALIGN, "sa_lookup_packed_factored: pointers must be 16-byte aligned");
+  (void)num_sms();
+  PLookupArgs a = {};
+  a.coords = coords; a.coords_bstride = coords_bstride;
+  a.HW = H * W; a.W3 = W3; a.nblk = packed_blocks(W3);
+  a.nl = normals_l; a.H = H; a.Wimg = W;
+  a.divisor = divisor; a.inv_divisor = (float)(1.0 / (double)divisor); a.post_scale = post_scale;
+  if (packed_a) {
+    a.packed[0] = packed_a; a.packed[1] = packed_normals_r; a.out[0] = out_a; a.out[1] = out_mono;
+    return launch_packed<2, -1, 1>(a, B, (cudaStream_t)stream);
+  }
+  a.packed[0] = packed_normals_r; a.out[0] = out_mono;
+  return launch_packed<1, -1, 0>(a, B, (cudaStream_t)stream);
 }

@@ -411,6 +411,44 @@ def _lookup_normals(packed_a: Optional[torch.Tensor], normals_l: torch.Tensor, n
     return out_a, out_m
 
 
+def _lookup_factored(packed_a: Optional[torch.Tensor], packed_nr: torch.Tensor, normals_l: torch.Tensor,
+                     post_scale: float, coords: torch.Tensor):
+    """Lookup with the mono volume in factored form (csrc/packed.cu, FV path): `packed_nr` is the packed pyramid
+    of the right normal map's B*3*H rows, `normals_l` the left normals.  Returns (out_a or None, out_mono)."""
+    coords, b, h, w = _coords_view(coords)
+    _cuda_f32(normals_l, "normals_l")
+    _cuda_f32(packed_nr, "packed right normals")
+    _req(normals_l.shape == (b, 3, h, w), "normals_l must be [B,3,H,W] matching coords")
+    _req(packed_nr.dim() == 2 and packed_nr.shape[0] == b * 3 * h and packed_nr.is_contiguous(),
+         "packed right normals must be [B*3*H, row floats]")
+    w3 = (packed_nr.shape[1] // 32 - 9) * 8
+    _req(w3 >= 8 and packed_row_floats(w3) == packed_nr.shape[1], "bad packed row size")
+    normals_l = normals_l.contiguous()
+    out_m = torch.empty((b, 36, h, w), dtype=torch.float32, device=coords.device)
+    out_a = None
+    if packed_a is not None:
+        _cuda_f32(packed_a, "packed pyramid")
+        _req(packed_a.shape == (b * h * w, packed_row_floats(w3)), "coords do not match the packed volume")
+        out_a = torch.empty_like(out_m)
+    lib = _lib.load()
+    divisor = float(torch.sqrt(torch.tensor(3)))
+    with _on(coords.device):
+        rc = lib.sa_lookup_packed_factored(packed_a.data_ptr() if packed_a is not None else None, packed_nr.data_ptr(),
+                                           normals_l.data_ptr(), divisor, float(post_scale), w3, coords.data_ptr(),
+                                           coords.stride(0), out_a.data_ptr() if out_a is not None else None,
+                                           out_m.data_ptr(), b, h, w, _stream_ptr(coords))
+    _lib.check(rc, "sa_lookup_packed_factored")
+    return out_a, out_m
+
+
+def _lookup_factored1(packed_nr, normals_l, post_scale, coords):
+    return _lookup_factored(None, packed_nr, normals_l, post_scale, coords)[1]
+
+
+def _lookup_packed_factored2(packed_a, packed_nr, normals_l, post_scale, coords):
+    return _lookup_factored(packed_a, packed_nr, normals_l, post_scale, coords)
+
+
 def _lookup_normals1(normals_l, normals_r, post_scale, coords):
     return _lookup_normals(None, normals_l, normals_r, post_scale, coords)[1]
 
@@ -542,6 +580,8 @@ _LIBDEF.define("volume_softargmax(Tensor vol) -> (Tensor, Tensor)")
 _LIBDEF.define("volume_entropy_conf(Tensor vol) -> (Tensor, Tensor)")
 _LIBDEF.define("lookup_normals(Tensor normals_l, Tensor normals_r, float post_scale, Tensor coords) -> Tensor")
 _LIBDEF.define("lookup_packed_normals2(Tensor packed_a, Tensor normals_l, Tensor normals_r, float post_scale, Tensor coords) -> (Tensor, Tensor)")
+_LIBDEF.define("lookup_factored(Tensor packed_nr, Tensor normals_l, float post_scale, Tensor coords) -> Tensor")
+_LIBDEF.define("lookup_packed_factored2(Tensor packed_a, Tensor packed_nr, Tensor normals_l, float post_scale, Tensor coords) -> (Tensor, Tensor)")
 _LIBDEF.define("lookup_packed(Tensor packed, int w3, Tensor coords) -> Tensor")
 _LIBDEF.define("lookup_packed2(Tensor packed_a, Tensor packed_b, int w3, Tensor coords) -> (Tensor, Tensor)")
 _LIBDEF.define("lookup_packed_conv(Tensor packed_a, Tensor packed_b, int w3, Tensor coords, Tensor weight, Tensor bias) -> (Tensor, Tensor)")
@@ -560,6 +600,8 @@ _LIBDEF.impl("volume_softargmax", _volume_softargmax, "CUDA")
 _LIBDEF.impl("volume_entropy_conf", _volume_entropy_conf, "CUDA")
 _LIBDEF.impl("lookup_normals", _lookup_normals1, "CUDA")
 _LIBDEF.impl("lookup_packed_normals2", _lookup_packed_normals2, "CUDA")
+_LIBDEF.impl("lookup_factored", _lookup_factored1, "CUDA")
+_LIBDEF.impl("lookup_packed_factored2", _lookup_packed_factored2, "CUDA")
 _LIBDEF.impl("lookup_packed", _lookup_packed1, "CUDA")
 _LIBDEF.impl("lookup_packed2", _lookup_packed2, "CUDA")
 _LIBDEF.impl("lookup_packed_conv", _lookup_packed_conv, "CUDA")
@@ -567,5 +609,5 @@ _LIBDEF.impl("truncate", _truncate, "CUDA")
 _LIBDEF.impl("masked_volume", _masked_volume, "CUDA")
 _LIBDEF.impl("corrupt", _corrupt, "CUDA")
 
-OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "corr_pack", "lookup_normals", "lookup_packed_normals2", "volume_softargmax", "volume_entropy_conf", "lookup_packed", "lookup_packed2", "lookup_packed_conv",
+OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "corr_pack", "lookup_normals", "lookup_packed_normals2", "lookup_factored", "lookup_packed_factored2", "volume_softargmax", "volume_entropy_conf", "lookup_packed", "lookup_packed2", "lookup_packed_conv",
             "truncate", "masked_volume", "corrupt"]

@@ -32,6 +32,16 @@ def sa():
     return sa_
 
 
+@pytest.fixture(autouse=True)
+def packed_mono_mode(sa):
+    """The bit-for-bit comparisons of `from_normals` in this module are statements about mono_mode "packed"; the
+    default "factored" mode has its own tests (`test_mono_lookup_factored`, the random-shape sweep)."""
+    B = sa.CorrBlockB200
+    old, B.mono_mode = B.mono_mode, "packed"
+    yield
+    B.mono_mode = old
+
+
 def normwise(got, ref):
     got = got.detach().double().cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got, dtype=np.float64)
     ref = ref.detach().double().cpu().numpy() if isinstance(ref, torch.Tensor) else np.asarray(ref, dtype=np.float64)
@@ -665,6 +675,10 @@ def test_fused_constructors_random_shapes(sa):
         ref = O.closed_lookup([lv.reshape(b, h, w2, -1) for lv in levels], coords[:, 0].cpu().numpy(), 4)
         assert maxabs(m_, ref) < 1e-5, (it, b, h, w2, w3)
         assert torch.equal(s_, two(coords))
+        B.mono_mode = "factored"   # (restored by the module's autouse fixture)
+        s_f, m_f = B.lookup_pair(one, B.from_normals(nl, nr), coords)
+        B.mono_mode = "packed"
+        assert maxabs(m_f, ref) < 1e-5 and maxabs(m_f, m_) <= 1e-6 and torch.equal(s_f, s_), (it, b, h, w2, w3)
 
 
 @pytest.mark.parametrize("shape", [(2, 5, 312, 312), (1, 3, 128, 128), (1, 2, 40, 40), (1, 2, 132, 264), (1, 1, 388, 520), (1, 2, 8, 8)])
@@ -703,6 +717,51 @@ def test_mono_lookup_on_the_fly_is_bit_identical(sa, shape):
     fa, fb = sa.lookup_pair_convc1(stereo, otf, coords, w, bias)
     ga, gb = sa.lookup_pair_convc1(stereo, pk, coords, w, bias)
     assert torch.equal(fb, gb) and torch.equal(fa, ga)
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 312, 312), (1, 3, 128, 128), (1, 2, 40, 40), (1, 2, 132, 264), (1, 1, 388, 520), (1, 2, 8, 8)])
+def test_mono_lookup_factored(sa, shape):
+    """`mono_mode = "factored"`: the lookup kernel combines three packed lines of the RIGHT NORMAL MAP with the
+    pixel's left normal (the mono volume has rank 3; pooling and packing are linear).  Agrees with the packed
+    mode to fp32 rounding (the scale sits on the coefficients; stored border entries are pooled before the
+    contraction) and with the float64 closed form as closely as the packed mode does."""
+    b, h, w2, w3 = shape
+    gen = torch.Generator().manual_seed(77 + w3)
+    nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w2, generator=gen), dim=1).to(DEV)
+    nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w3, generator=gen), dim=1).to(DEV)
+    B = sa.CorrBlockB200
+    old = B.mono_mode
+    try:
+        B.mono_mode = "factored"
+        fc = B.from_normals(nl, nr)
+        assert fc._packed is None and fc._packed_nr is not None and fc._packed_nr.shape[0] == b * 3 * h
+        B.mono_mode = "packed"
+        pk = B.from_normals(nl, nr)
+    finally:
+        B.mono_mode = old
+    stereo = B(torch.randn(b, h, w2, 1, w3, generator=gen).to(DEV))
+    levels = O.closed_pyramid(pk.fullcorr.squeeze(3).cpu().numpy(), 4)[:4]
+    levels = [lv.reshape(b, h, w2, -1) for lv in levels]
+    x = torch.arange(w2, dtype=torch.float32).view(1, 1, 1, w2).expand(b, 1, h, w2) * (w3 / w2)
+    for kind, dx in (("left", -torch.rand(b, 1, h, w2, generator=gen) * (w3 / 3)), ("right", torch.rand(b, 1, h, w2, generator=gen) * 60),
+                     ("far", (torch.rand(b, 1, h, w2, generator=gen) - 0.5) * 4 * w3), ("int", -torch.randint(0, 9, (b, 1, h, w2), generator=gen).float())):
+        coords = torch.cat([x + dx, torch.zeros(b, 1, h, w2)], 1).to(DEV)
+        want = pk(coords)
+        got = fc(coords)
+        assert float((got - want).abs().max()) <= 1e-6, kind         # |V| <= 1: a few ulp
+        ref = O.closed_lookup(levels, coords[:, 0].cpu().numpy(), 4)
+        assert maxabs(got, ref) < 5e-6, kind
+        s1, m1 = B.lookup_pair(stereo, fc, coords)
+        s2, m2 = B.lookup_pair(stereo, pk, coords)
+        assert torch.equal(m1, got) and torch.equal(s1, s2), kind
+    # consumers that need the packed volume get it on demand; the reference attributes still work
+    assert torch.equal(fc.fullcorr, pk.fullcorr)
+    w = (torch.randn(64, 36, 1, 1, generator=gen) / 6).to(DEV)
+    bias = torch.zeros(64, device=DEV)
+    fa, fb = sa.lookup_pair_convc1(stereo, fc, coords, w, bias)
+    ga, gb = sa.lookup_pair_convc1(stereo, pk, coords, w, bias)
+    assert torch.equal(fb, gb) and torch.equal(fa, ga)
+    assert fc._packed is not None and fc._packed_nr is None
 
 
 def test_more_than_2_31_packed_floats(sa):

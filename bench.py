@@ -478,7 +478,7 @@ def run_gpu(args):
             "kernels": kernels,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(result), flush=True)
+        emit(result)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -633,7 +633,7 @@ def run_tiled(args):
         ms = float(t.item())
     if rank == 0:
         ms_step = ms / args.steps
-        print(json.dumps({
+        emit({
             "metric": "stereo pairs/sec @1984x2872 tiled (cost-volume path per tile, 32 iters)", "value": round(args.images / (ms_step / 1e3), 3),
             "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": f"{args.precision} corr, f32 pyramid/lookup",
@@ -643,7 +643,7 @@ def run_tiled(args):
                                            "parallelism": (f"tiles sharded x{world}, stitch = reduce + normalise + gather over NVLink peer memory, one "
                                                            f"kernel per rank (sa_peer_reduce), side stream") if stitcher is not None else
                                                           f"tiles sharded x{world}, one async NCCL reduce(sum) of [images,H,W] per step"},
-        }), flush=True)
+        })
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -713,7 +713,7 @@ def run_reference(args):
     value = pairs * args.steps / t
     sample = (f"each step = {pairs} of {b} pairs of {args.workload}, all {ITERS} iterations, oracle port of the "
               f"reference op sequence (einsum, avg_pool2d, grid_sample) on CPU")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": metric_for(args.workload), "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(t / args.steps * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -721,10 +721,30 @@ def run_reference(args):
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
+
+
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line when the
+    box sets NCCL_DEBUG), so the real stdout is kept aside for `emit` and file descriptor 1 is pointed at stderr."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -163,8 +163,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 
 class GpuPath:
-    def __init__(self, sa, d, variant):
-        self.sa, self.d, self.variant = sa, d, variant
+    def __init__(self, sa, d, variant, mono="factored"):
+        self.sa, self.d, self.variant, self.mono = sa, d, variant, mono
         self.ev = None  # (start, end) events around the lookup loop of the current step
         self.launches = 0
 
@@ -175,8 +175,14 @@ class GpuPath:
 
     def build_mono(self):
         B, d = self.sa.CorrBlockB200, self.d
+        if self.mono == "aggregated":
+            # the README's configuration (--use_aggregate_mono_vol): the mono volume is materialised (it feeds the
+            # hourglass, stereoanywhere.py:136-165) and the block is built from a dense volume - here the A2 volume
+            # itself stands in for the hourglass output, an arbitrary [B,H,W,1,W] tensor
+            self.launches += 2
+            return B(B.mono_corr(d["nl"], d["nr"]), radius=RADIUS, num_levels=LEVELS)
         if B.mono_mode != "otf":
-            self.launches += 1   # packed: one pack kernel; on the fly: nothing to launch, the lookups read the normals
+            self.launches += 1   # packed / factored: one pack kernel; on the fly: nothing to launch
         return B.from_normals(d["nl"], d["nr"], radius=RADIUS, num_levels=LEVELS)
 
     def build(self):
@@ -239,13 +245,13 @@ def run_gpu(args):
     import stereoanywhere_b200 as sa
 
     sa.CorrBlockB200.precision = args.precision
-    sa.CorrBlockB200.mono_mode = args.mono
+    sa.CorrBlockB200.mono_mode = args.mono if args.mono != "aggregated" else "packed"
     otf = args.variant == "fused" and args.mono == "otf"
     factored = args.variant == "fused" and args.mono == "factored"
     b, c, h, w = WORKLOADS[args.workload]
     host, d = make_inputs(b, c, h, w, dev, seed=rank, pinned=True)
     torch.cuda.synchronize()
-    path = GpuPath(sa, d, args.variant)
+    path = GpuPath(sa, d, args.variant, args.mono)
 
     def barrier():
         if dist is not None:
@@ -335,7 +341,8 @@ def run_gpu(args):
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
-    launches = path.launches if g_build is None else args.steps * ((33 if otf else 34) if args.variant == "fused" else 69)
+    launches = path.launches if g_build is None else args.steps * (
+        (33 if otf else 35 if args.mono == "aggregated" else 34) if args.variant == "fused" else 69)
     lk_ms = sum(a.elapsed_time(bb) for a, bb in lk_events) / args.steps
     breakdown = None
     if g_build is not None and args.variant == "fused":
@@ -364,7 +371,7 @@ def run_gpu(args):
     res_m = torch.empty_like(res_s).pin_memory()
     h2d = sum(host[k].numel() * 4 for k in keys)
     d2h = res_s.numel() * 4 * 2
-    paths = [GpuPath(sa, sset, args.variant) for sset in sets]
+    paths = [GpuPath(sa, sset, args.variant, args.mono) for sset in sets]
     copy_stream = torch.cuda.Stream()
     main_stream = torch.cuda.current_stream()
     ready = [torch.cuda.Event() for _ in range(2)]   # upload of set i finished
@@ -428,7 +435,7 @@ def run_gpu(args):
         achieved = alg / (lk_launch_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "lookup_packed_kernel" + ("<NV=2>" if args.variant == "fused" else "<NV=1>"),
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": TRAFFIC_BYTES.get((args.workload, args.variant, args.mono)), "peak_source": peak_src,
+                "traffic": TRAFFIC_BYTES.get((args.workload, args.variant, "packed" if args.mono == "aggregated" else args.mono)), "peak_source": peak_src,
                 "algorithmic_bytes_per_pixel": alg_px,
                 "algorithmic_bytes_per_launch": alg, "launch_us": round(lk_launch_ms * 1e3, 2),
                 "path_algorithmic_gbs": round(path_bytes(b, c, h, w) / (ms_step * 1e-3) / 1e9, 1)}
@@ -438,6 +445,8 @@ def run_gpu(args):
             mo_us = breakdown[1] * 1e3 if breakdown[1] is not None else None
             packed = p * (w // 8 + 9) * 128
             mono_bytes = 3 * b * h * (w // 8 + 9) * 128 + 3 * b * h * w * 4 if factored else packed
+            if args.mono == "aggregated":   # volume written, read again, packed
+                mono_bytes = 2 * p * w * 4 + packed
             tf32_peak = tensor_peak_tf32()
             tflops = 2.0 * p * w * c / (st_us * 1e-6) / 1e12
             kernels = {
@@ -448,7 +457,9 @@ def run_gpu(args):
                                    "note": "HBM-bound by the packed write; the tensor pipe is reported, not targeted"},
                 "pack_normals": ({"us": round(mo_us, 1), "hbm_gbs": round(mono_bytes / mo_us / 1e3, 1),
                                   "hbm_frac": round(mono_bytes / mo_us / 1e3 / peak, 4),
-                                  **({"note": "factored: only the right normal map's rows are packed (launch-bound)"} if factored else {})}
+                                  **({"note": "factored: only the right normal map's rows are packed (launch-bound)"} if factored else {}),
+                                  **({"note": "two kernels: A2 volume materialised (stand-in for the hourglass output), "
+                                              "then sa_pack_pyramid of the dense volume"} if args.mono == "aggregated" else {})}
                                  if mo_us is not None else
                                  "not launched: the mono lookups are computed from the normal maps inside the lookup kernel"),
                 "lookup_packed2": {"us": round(lk_launch_ms * 1e3, 2), "launches": n_lk_launch,
@@ -467,7 +478,9 @@ def run_gpu(args):
                        "mono": ("on the fly: lookups computed from the normal maps inside the lookup kernel, bit-identical to "
                                 "the packed pyramid (no mono volume / pyramid in memory)") if otf else
                                ("factored: packed pyramid of the right normal map's rows (rank-3 volume, linear pyramid); "
-                                "the lookup combines three lines with the pixel's left normal") if factored else "packed pyramid",
+                                "the lookup combines three lines with the pixel's left normal") if factored else
+                               ("aggregated (README configuration): dense mono volume materialised, block built from a "
+                                "dense volume") if args.mono == "aggregated" else "packed pyramid",
                        "l2": "inputs+volumes (>1 GB/step) exceed the 126 MB L2; no explicit flush",
                        "parallelism": f"batch-sharded x{world}, async all_gather of quarter-res disparity per step"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -510,7 +523,7 @@ def run_tiled(args):
     from stereoanywhere_b200 import tiling
 
     sa.CorrBlockB200.precision = args.precision
-    sa.CorrBlockB200.mono_mode = args.mono
+    sa.CorrBlockB200.mono_mode = args.mono if args.mono != "aggregated" else "packed"
     B = sa.CorrBlockB200
     H, W = 1984, 2880                      # 1984x2872 replicate-padded to /32 (test_mapreduce_v2.py:217-227)
     th, tw, ov = tiling.PRESETS[args.tile_preset]
@@ -759,9 +772,10 @@ def main():
     ap.add_argument("--variant", default="fused", choices=["fused", "protocol"],
                     help="fused: truncate= / mono_corr / lookup_pair entry points; protocol: the reference's exact call sequence")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"], help="stereo correlation kernel")
-    ap.add_argument("--mono", default="factored", choices=["otf", "packed", "factored"],
+    ap.add_argument("--mono", default="factored", choices=["otf", "packed", "factored", "aggregated"],
                     help="mono block of the fused variant: factored (packed right normals, combined inside the lookup), "
-                         "the packed pyramid of the volume, or lookups computed on the fly from the normals")
+                         "the packed pyramid of the volume, lookups computed on the fly from the normals, or 'aggregated': "
+                         "the README configuration, block built from a dense (hourglass-output-like) volume")
     ap.add_argument("--graph", type=int, default=1, help="replay the step from a CUDA graph in the device-resident run")
     ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

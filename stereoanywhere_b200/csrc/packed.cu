@@ -211,6 +211,7 @@ struct PLookupArgs {
   const float* nr;
   int H, Wimg;
   float divisor, inv_divisor, post_scale;
+  int B;  // batch (the pipelined kernel walks (b, tile) pairs itself)
   // factored mono volume (FV >= 0): packed[FV] holds the packed pyramid of the RIGHT NORMAL MAP's rows,
   // [(b*3 + c)*H + h][nblk][32]; nl / H / Wimg / divisor / inv_divisor / post_scale as above
 };
@@ -225,6 +226,71 @@ __device__ __forceinline__ void shift_if(float (&v)[N], bool on, int by, int kee
 #pragma unroll
   for (int i = 0; i < N; ++i)
     if (i < keep && i + by < N) v[i] = on ? v[i + by] : v[i];
+}
+
+// One staged line (32 floats, chunk c of pixel p at chunk c ^ (p & 7)) -> the window entries of the four levels:
+// L0[8q-4..8q+12], L1[4q-4..4q+8], L2[2q-4..2q+6], L3[q-4..q+5]; the entries that are not stored are re-derived
+// with the pyramid's own 0.5 (a + b).
+__device__ __forceinline__ void line_levels(const float* src, int p, float (&l0)[17], float (&l1)[13], float (&l2)[11],
+                                            float (&l3)[10]) {
+  float ln[32];
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    const float4 t = *reinterpret_cast<const float4*>(src + ((ch ^ (p & 7)) << 2));
+    ln[4 * ch] = t.x; ln[4 * ch + 1] = t.y; ln[4 * ch + 2] = t.z; ln[4 * ch + 3] = t.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 17; ++i) l0[i] = ln[i];
+  // slots 17..31: full windows of levels 1..3 (relative index 0 = first stored entry of the level)
+  l1[0] = ln[17]; l1[1] = ln[18]; l1[10] = ln[19]; l1[11] = ln[20]; l1[12] = ln[21];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) l1[2 + t] = (l0[2 * t] + l0[2 * t + 1]) * 0.5f;
+  l2[0] = ln[22]; l2[1] = ln[23]; l2[8] = ln[24]; l2[9] = ln[25]; l2[10] = ln[26];
+#pragma unroll
+  for (int t = 0; t < 6; ++t) l2[2 + t] = (l1[2 * t] + l1[2 * t + 1]) * 0.5f;
+  l3[0] = ln[27]; l3[1] = ln[28]; l3[7] = ln[29]; l3[8] = ln[30]; l3[9] = ln[31];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) l3[2 + t] = (l2[2 * t] + l2[2 * t + 1]) * 0.5f;
+}
+
+// The 4 x 9 taps at x from the window entries (which are consumed): put(channel, value).
+template <class Put>
+__device__ __forceinline__ void blend_windows(float (&l0)[17], float (&l1)[13], float (&l2)[11], float (&l3)[10], float x,
+                                              Put put) {
+  const float flx = fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
+  const int x0 = (int)flx;
+  // window starts inside the stored ranges: a0 in [0,8), a1 in [0,4), a2 in [0,2), a3 = 0
+  {
+    shift_if(l0, (x0 & 1) != 0, 1, 16);
+    shift_if(l0, (x0 & 2) != 0, 2, 14);
+    shift_if(l0, (x0 & 4) != 0, 4, 10);
+    const float f = x - floorf(x);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) put(k, blend(l0[k], l0[k + 1], f));
+  }
+  {
+    const int x1 = x0 >> 1;
+    shift_if(l1, (x1 & 1) != 0, 1, 12);
+    shift_if(l1, (x1 & 2) != 0, 2, 10);
+    const float xs = x * 0.5f;
+    const float f = xs - floorf(xs);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) put(9 + k, blend(l1[k], l1[k + 1], f));
+  }
+  {
+    const int x2 = x0 >> 2;
+    shift_if(l2, (x2 & 1) != 0, 1, 10);
+    const float xs = x * 0.25f;
+    const float f = xs - floorf(xs);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) put(18 + k, blend(l2[k], l2[k + 1], f));
+  }
+  {
+    const float xs = x * 0.125f;
+    const float f = xs - floorf(xs);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) put(27 + k, blend(l3[k], l3[k + 1], f));
+  }
 }
 
 // OTF = index of a volume that is not read from a packed array but COMPUTED from the C = 3 normal maps (the mono
@@ -414,73 +480,11 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
       }
     }
   } else {
-    float e[15];  // slots 17..31 of the line
-    const float* src = buf + tid * 32;  // unit index == tid
-    float ln[32];
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-      const float4 t = *reinterpret_cast<const float4*>(src + ((ch ^ (p & 7)) << 2));
-      ln[4 * ch] = t.x; ln[4 * ch + 1] = t.y; ln[4 * ch + 2] = t.z; ln[4 * ch + 3] = t.w;
-    }
-#pragma unroll
-    for (int i = 0; i < 17; ++i) l0[i] = ln[i];
-#pragma unroll
-    for (int i = 0; i < 15; ++i) e[i] = ln[17 + i];
-    // full windows of levels 1..3 (relative index 0 = first stored entry of the level)
-    l1[0] = e[0]; l1[1] = e[1]; l1[10] = e[2]; l1[11] = e[3]; l1[12] = e[4];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) l1[2 + t] = (l0[2 * t] + l0[2 * t + 1]) * 0.5f;
-    l2[0] = e[5]; l2[1] = e[6]; l2[8] = e[7]; l2[9] = e[8]; l2[10] = e[9];
-#pragma unroll
-    for (int t = 0; t < 6; ++t) l2[2 + t] = (l1[2 * t] + l1[2 * t + 1]) * 0.5f;
-    l3[0] = e[10]; l3[1] = e[11]; l3[7] = e[12]; l3[8] = e[13]; l3[9] = e[14];
-#pragma unroll
-    for (int t = 0; t < 5; ++t) l3[2 + t] = (l2[2 * t] + l2[2 * t + 1]) * 0.5f;
+    line_levels(buf + tid * 32, p, l0, l1, l2, l3);  // unit index == tid
   }
   __syncthreads();  // staging is dead: `buf` becomes the [channel][pixel] output tile
 
-  const float x = s_x[p];
-  const float flx = fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
-  const int x0 = (int)flx;
-  // window starts inside the stored ranges: a0 in [0,8), a1 in [0,4), a2 in [0,2), a3 = 0
-  {
-    float w[17];
-#pragma unroll
-    for (int i = 0; i < 17; ++i) w[i] = l0[i];
-    shift_if(w, (x0 & 1) != 0, 1, 16);
-    shift_if(w, (x0 & 2) != 0, 2, 14);
-    shift_if(w, (x0 & 4) != 0, 4, 10);
-    const float f = x - floorf(x);
-    float* so = buf + (v * NC + 0) * SP + p;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) so[k * SP] = blend(w[k], w[k + 1], f);
-  }
-  {
-    const int x1 = x0 >> 1;
-    shift_if(l1, (x1 & 1) != 0, 1, 12);
-    shift_if(l1, (x1 & 2) != 0, 2, 10);
-    const float xs = x * 0.5f;
-    const float f = xs - floorf(xs);
-    float* so = buf + (v * NC + 9) * SP + p;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) so[k * SP] = blend(l1[k], l1[k + 1], f);
-  }
-  {
-    const int x2 = x0 >> 2;
-    shift_if(l2, (x2 & 1) != 0, 1, 10);
-    const float xs = x * 0.25f;
-    const float f = xs - floorf(xs);
-    float* so = buf + (v * NC + 18) * SP + p;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) so[k * SP] = blend(l2[k], l2[k + 1], f);
-  }
-  {
-    const float xs = x * 0.125f;
-    const float f = xs - floorf(xs);
-    float* so = buf + (v * NC + 27) * SP + p;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) so[k * SP] = blend(l3[k], l3[k + 1], f);
-  }
+  blend_windows(l0, l1, l2, l3, s_x[p], [&](int c, float val) { buf[(v * NC + c) * SP + p] = val; });
   __syncthreads();
 
   // ---- [channel][pixel] tile -> NCHW
@@ -511,6 +515,203 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pipelined form of the dual lookup (NV = 2; FV = 1: factored mono volume, FV = -1: two packed volumes).
+// lookup_packed_kernel is latency-bound: a CTA lives through coordinate load -> barrier -> line loads -> barrier
+// -> blend -> barrier -> stores, and with 2.7 waves of CTAs per launch nothing hides the two dependent DRAM round
+// trips.  Here a CTA is persistent and works on three tiles at once: while tile k is blended and stored, the lines
+// of tile k+1 are in flight (cp.async into the other stage buffer; the right-normal lines of the factored form are
+// held in registers across the blend) and the coordinates / left normals of tile k+2 are being loaded.  Two
+// barriers per tile; per-tile metadata (x, block, scaled normals) lives in three rotating shared-memory slots.
+// ---------------------------------------------------------------------------------------------
+template <int TILE, int FV>
+__global__ void __launch_bounds__(2 * TILE) lookup_pipe_kernel(const PLookupArgs a) {
+  constexpr int NV = 2, THREADS = NV * TILE, NC = 36, SP = TILE + 4;
+  constexpr int STAGE = NV * TILE * 32;       // floats per stage buffer
+  constexpr int OUT = NV * NC * SP;           // floats of the [channel][pixel] output tile
+  constexpr int META = 6 * TILE;              // floats per metadata slot: x, blk, float4 n
+  constexpr int UPS = THREADS / 8, SPV = 8 / NV;
+  static_assert(FV == 1 || FV == -1, "mono volume: factored or packed");
+  extern __shared__ __align__(16) float smem[];
+  float* const stage = smem;                  // [2][STAGE]
+  float* const tile = smem + 2 * STAGE;       // [OUT]
+  float* const meta = tile + OUT;             // [3][META]
+
+  const int tid = threadIdx.x;
+  const int p = tid % TILE, v = tid / TILE;
+  const int ch = tid & 7, u0 = tid >> 3;
+  const int tiles_x = (a.HW + TILE - 1) / TILE;
+  const long long ntiles = (long long)tiles_x * a.B;
+  const long long stride = gridDim.x;
+  const long long plane = (long long)a.H * a.Wimg;  // == HW
+  const int cplane = FV >= 0 ? a.H * a.nblk * 32 : 0;
+  const float kscale = a.post_scale * a.inv_divisor;
+
+  float rx = 0.f, rn0 = 0.f, rn1 = 0.f, rn2 = 0.f;  // coordinates / left normal of the tile two ahead (tid < TILE)
+
+  auto load_meta = [&](long long t) {
+    rx = rn0 = rn1 = rn2 = 0.f;
+    if (tid < TILE && t < ntiles) {
+      const int b = (int)(t / tiles_x);
+      const int hw = (int)(t - (long long)b * tiles_x) * TILE + tid;
+      if (hw < a.HW) {
+        rx = __ldg(a.coords + (long long)b * a.coords_bstride + hw);
+        if (FV >= 0) {
+          const float* nlp = a.nl + (long long)b * 3 * plane + hw;
+          rn0 = __ldg(nlp); rn1 = __ldg(nlp + plane); rn2 = __ldg(nlp + 2 * plane);
+        }
+      }
+    }
+  };
+  auto write_meta = [&](long long t, float* m) {  // from the registers filled by load_meta(t)
+    if (tid < TILE) {
+      int blk = -1, hw = 0;
+      if (t < ntiles) {
+        const int b = (int)(t / tiles_x);
+        hw = (int)(t - (long long)b * tiles_x) * TILE + tid;
+        if (hw < a.HW) {
+          const float fl = fminf(fmaxf(floorf(rx), -1.0e6f), 1.0e6f);
+          const int q = ((int)fl >> 3) - kQMin;
+          if (q >= 0 && q < a.nblk) blk = q;
+        }
+      }
+      m[tid] = rx;
+      reinterpret_cast<int*>(m)[TILE + tid] = blk;
+      if (FV >= 0) {
+        const float k = blk >= 0 ? kscale : 0.f;
+        const int off = blk >= 0 ? ((hw / a.Wimg) * a.nblk + blk) * 32 : 0;
+        reinterpret_cast<float4*>(m + 2 * TILE)[tid] = make_float4(rn0 * k, rn1 * k, rn2 * k, __int_as_float(off));
+      }
+    }
+  };
+  float4 r[SPV][3];  // factored form: this thread's chunks of the three right-normal lines of its SPV pixels
+  auto issue_lines = [&](long long t, const float* m, float* stg) {
+    const int b = (int)(t / tiles_x);
+    const int hw0 = (int)(t - (long long)b * tiles_x) * TILE;
+    const long long row0 = (long long)b * a.HW + hw0;
+    const int* s_blk = reinterpret_cast<const int*>(m) + TILE;
+#pragma unroll
+    for (int mm = 0; mm < SPV; ++mm) {
+      const int pm = u0 + mm * UPS;
+      const int blk = s_blk[pm];
+      const long long goff = blk >= 0 ? ((row0 + pm) * (long long)a.nblk + blk) * 32 + ch * 4 : -1;
+#pragma unroll
+      for (int vv = 0; vv < NV; ++vv) {
+        if (vv == FV) continue;
+        float* dst = stg + (vv * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2);
+        if (goff >= 0)
+          cp_async16(dst, (vv ? a.packed[1] : a.packed[0]) + goff);
+        else
+          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (FV >= 0) {
+      const float* rp = a.packed[FV >= 0 ? FV : 0] + (long long)b * 3 * cplane + ch * 4;
+      const float4* s_n = reinterpret_cast<const float4*>(m + 2 * TILE);
+#pragma unroll
+      for (int mm = 0; mm < SPV; ++mm) {
+        const int off = __float_as_int(s_n[u0 + mm * UPS].w);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) r[mm][c] = __ldg(reinterpret_cast<const float4*>(rp + (off + c * cplane)));
+      }
+    }
+  };
+  auto combine_lines = [&](const float* m, float* stg) {  // factored form: r -> the mono half of the stage buffer
+    const float4* s_n = reinterpret_cast<const float4*>(m + 2 * TILE);
+#pragma unroll
+    for (int mm = 0; mm < SPV; ++mm) {
+      const int pm = u0 + mm * UPS;
+      const float4 n = s_n[pm];
+      float4 o;
+      o.x = fmaf(n.z, r[mm][2].x, fmaf(n.y, r[mm][1].x, n.x * r[mm][0].x));
+      o.y = fmaf(n.z, r[mm][2].y, fmaf(n.y, r[mm][1].y, n.x * r[mm][0].y));
+      o.z = fmaf(n.z, r[mm][2].z, fmaf(n.y, r[mm][1].z, n.x * r[mm][0].z));
+      o.w = fmaf(n.z, r[mm][2].w, fmaf(n.y, r[mm][1].w, n.x * r[mm][0].w));
+      *reinterpret_cast<float4*>(stg + (FV * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2)) = o;
+    }
+  };
+
+  long long t = blockIdx.x;
+  if (t >= ntiles) return;
+  int s0 = 0, s1 = 1, s2 = 2;  // metadata slots of tiles k, k+1, k+2
+  // prologue: tile 0's metadata and lines, tile 1's coordinates
+  load_meta(t);
+  write_meta(t, meta + s0 * META);
+  load_meta(t + stride);
+  __syncthreads();
+  issue_lines(t, meta + s0 * META, stage);
+  if (FV >= 0) combine_lines(meta + s0 * META, stage);
+
+  for (int k = 0; t < ntiles; ++k, t += stride) {
+    const long long tn = t + stride;
+    float* const cur = stage + (k & 1) * STAGE;
+    float* const nxt = stage + ((k & 1) ^ 1) * STAGE;
+    write_meta(tn, meta + s1 * META);   // registers hold tile k+1's coordinates
+    load_meta(tn + stride);             // tile k+2's, in flight during this iteration
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // tile k's lines and tile k+1's metadata visible; the output tile is free again
+    if (tn < ntiles) issue_lines(tn, meta + s1 * META, nxt);
+
+    {  // blend tile k: thread (pixel p, volume v)
+      float l0[17], l1[13], l2[11], l3[10];
+      line_levels(cur + tid * 32, p, l0, l1, l2, l3);
+      blend_windows(l0, l1, l2, l3, meta[s0 * META + p], [&](int c, float val) { tile[(v * NC + c) * SP + p] = val; });
+    }
+    if (FV >= 0 && tn < ntiles) combine_lines(meta + s1 * META, nxt);
+    __syncthreads();
+
+    {  // [channel][pixel] tile -> NCHW (HW % 4 == 0: the launcher falls back to lookup_packed_kernel otherwise)
+      const int b = (int)(t / tiles_x);
+      const int hw0 = (int)(t - (long long)b * tiles_x) * TILE;
+      const int npx = min(TILE, a.HW - hw0);
+      constexpr int T4 = TILE / 4;
+      static_assert(THREADS == 4 * NV * T4 && NC % 4 == 0, "store mapping");
+      const int c0 = tid / T4, tt = (tid % T4) * 4;
+      if (tt < npx) {
+        const long long pix = (long long)b * NC * a.HW + hw0 + tt;
+        const long long cstride = (long long)a.HW;
+#pragma unroll
+        for (int kk = 0; kk < NC / 4; ++kk) {
+          const int c = c0 + 4 * NV * kk;          // 0 .. NV*NC-1
+          const int vv = c >= NC ? 1 : 0;
+          const int cc = c - vv * NC;
+          const float4 val = *reinterpret_cast<const float4*>(tile + c * SP + tt);
+          st_stream_v4((vv ? a.out[1] : a.out[0]) + pix + cc * cstride, val);
+        }
+      }
+    }
+    const int s = s0; s0 = s1; s1 = s2; s2 = s;
+  }
+}
+
+template <int TILE, int FV>
+static int launch_pipe(const PLookupArgs& a, cudaStream_t st) {
+  constexpr int NV = 2, NC = 36, SP = TILE + 4;
+  const size_t smem = (size_t)(2 * NV * TILE * 32 + NV * NC * SP + 3 * 6 * TILE) * sizeof(float);
+  auto kern = lookup_pipe_kernel<TILE, FV>;
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) SA_FAIL((int)e, "sa_lookup_packed: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, NV * TILE, smem);
+    if (e != cudaSuccess || n < 1) SA_FAIL(e != cudaSuccess ? (int)e : SA_E_UNSUPPORTED, "sa_lookup_packed: occupancy query failed");
+    if (getenv("SA_B200_LOOKUP_PIPE_CTAS")) n = min(n, max(1, atoi(getenv("SA_B200_LOOKUP_PIPE_CTAS"))));
+    per_sm = n;
+  }
+  const long long ntiles = (long long)((a.HW + TILE - 1) / TILE) * a.B;
+  const long long cap = (long long)num_sms() * per_sm;
+  kern<<<(unsigned)(ntiles < cap ? ntiles : cap), NV * TILE, smem, st>>>(a);
+  return finish_launch("sa_lookup_packed");
+}
+
+// 0: lookup_packed_kernel; 1: the pipelined kernel for dual lookups (SA_B200_LOOKUP_PIPE)
+static int pipe_mode() {
+  static const int m = getenv("SA_B200_LOOKUP_PIPE") ? atoi(getenv("SA_B200_LOOKUP_PIPE")) : 0;
+  return m;
 }
 
 template <int NV, int TILE, int OTF, int FV>
@@ -608,7 +809,9 @@ extern "C" int sa_lookup_packed(const float* packed_a, const float* packed_b, in
   a.packed[0] = packed_a; a.packed[1] = packed_b;
   a.out[0] = out_a; a.out[1] = out_b;
   a.coords = coords; a.coords_bstride = coords_bstride;
-  a.HW = H * W; a.W3 = W3; a.nblk = packed_blocks(W3);
+  a.HW = H * W; a.W3 = W3; a.nblk = packed_blocks(W3); a.B = B;
+  if (packed_b && pipe_mode() && (a.HW & 3) == 0)
+    return pipe_mode() == 64 ? launch_pipe<64, -1>(a, (cudaStream_t)stream) : launch_pipe<32, -1>(a, (cudaStream_t)stream);
   return packed_b ? launch_packed<2, -1>(a, B, (cudaStream_t)stream) : launch_packed<1, -1>(a, B, (cudaStream_t)stream);
 }
 
@@ -656,7 +859,9 @@ extern "C" int sa_lookup_packed_factored(const float* packed_a, const float* pac
   a.nl = normals_l; a.H = H; a.Wimg = W;
   a.divisor = divisor; a.inv_divisor = (float)(1.0 / (double)divisor); a.post_scale = post_scale;
   if (packed_a) {
-    a.packed[0] = packed_a; a.packed[1] = packed_normals_r; a.out[0] = out_a; a.out[1] = out_mono;
+    a.packed[0] = packed_a; a.packed[1] = packed_normals_r; a.out[0] = out_a; a.out[1] = out_mono; a.B = B;
+    if (pipe_mode() && (a.HW & 3) == 0)
+      return pipe_mode() == 64 ? launch_pipe<64, 1>(a, (cudaStream_t)stream) : launch_pipe<32, 1>(a, (cudaStream_t)stream);
     return launch_packed<2, -1, 1>(a, B, (cudaStream_t)stream);
   }
   a.packed[0] = packed_normals_r; a.out[0] = out_mono;

@@ -526,11 +526,14 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
 // held in registers across the blend) and the coordinates / left normals of tile k+2 are being loaded.  Two
 // barriers per tile; per-tile metadata (x, block, scaled normals) lives in three rotating shared-memory slots.
 // ---------------------------------------------------------------------------------------------
-template <int TILE, int FV>
-__global__ void __launch_bounds__(2 * TILE) lookup_pipe_kernel(const PLookupArgs a) {
+// DIRECT: results go straight from registers to NCHW (one 128-byte line per warp store), no output tile and no
+// second barrier - 18.7 KB instead of 28.7 KB of shared memory per CTA.  HOLD: the factored form keeps the loaded
+// right-normal chunks in registers across the blend (false: combines them at once).
+template <int TILE, int FV, bool DIRECT, bool HOLD>
+__global__ void __launch_bounds__(2 * TILE, DIRECT ? 12 : 7) lookup_pipe_kernel(const PLookupArgs a) {
   constexpr int NV = 2, THREADS = NV * TILE, NC = 36, SP = TILE + 4;
   constexpr int STAGE = NV * TILE * 32;       // floats per stage buffer
-  constexpr int OUT = NV * NC * SP;           // floats of the [channel][pixel] output tile
+  constexpr int OUT = DIRECT ? 0 : NV * NC * SP;  // floats of the [channel][pixel] output tile
   constexpr int META = 6 * TILE;              // floats per metadata slot: x, blk, float4 n
   constexpr int UPS = THREADS / 8, SPV = 8 / NV;
   static_assert(FV == 1 || FV == -1, "mono volume: factored or packed");
@@ -653,17 +656,31 @@ __global__ void __launch_bounds__(2 * TILE) lookup_pipe_kernel(const PLookupArgs
     load_meta(tn + stride);             // tile k+2's, in flight during this iteration
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();  // tile k's lines and tile k+1's metadata visible; the output tile is free again
-    if (tn < ntiles) issue_lines(tn, meta + s1 * META, nxt);
+    if (tn < ntiles) {
+      issue_lines(tn, meta + s1 * META, nxt);
+      if (FV >= 0 && !HOLD) combine_lines(meta + s1 * META, nxt);
+    }
 
     {  // blend tile k: thread (pixel p, volume v)
       float l0[17], l1[13], l2[11], l3[10];
       line_levels(cur + tid * 32, p, l0, l1, l2, l3);
-      blend_windows(l0, l1, l2, l3, meta[s0 * META + p], [&](int c, float val) { tile[(v * NC + c) * SP + p] = val; });
+      if (DIRECT) {
+        const int b = (int)(t / tiles_x);
+        const int hw0 = (int)(t - (long long)b * tiles_x) * TILE;
+        float* const gout = (v ? a.out[1] : a.out[0]) + (long long)b * NC * a.HW + hw0 + p;
+        const long long cstride = a.HW;
+        const bool live = hw0 + p < a.HW;
+        blend_windows(l0, l1, l2, l3, meta[s0 * META + p], [&](int c, float val) {
+          if (live) st_stream_f32(gout + c * cstride, val);
+        });
+      } else {
+        blend_windows(l0, l1, l2, l3, meta[s0 * META + p], [&](int c, float val) { tile[(v * NC + c) * SP + p] = val; });
+      }
     }
-    if (FV >= 0 && tn < ntiles) combine_lines(meta + s1 * META, nxt);
-    __syncthreads();
-
-    {  // [channel][pixel] tile -> NCHW (HW % 4 == 0: the launcher falls back to lookup_packed_kernel otherwise)
+    if (FV >= 0 && HOLD && tn < ntiles) combine_lines(meta + s1 * META, nxt);
+    if (!DIRECT) {
+      __syncthreads();
+      // [channel][pixel] tile -> NCHW (HW % 4 == 0: the launcher falls back to lookup_packed_kernel otherwise)
       const int b = (int)(t / tiles_x);
       const int hw0 = (int)(t - (long long)b * tiles_x) * TILE;
       const int npx = min(TILE, a.HW - hw0);
@@ -687,11 +704,11 @@ __global__ void __launch_bounds__(2 * TILE) lookup_pipe_kernel(const PLookupArgs
   }
 }
 
-template <int TILE, int FV>
+template <int TILE, int FV, bool DIRECT, bool HOLD>
 static int launch_pipe(const PLookupArgs& a, cudaStream_t st) {
   constexpr int NV = 2, NC = 36, SP = TILE + 4;
-  const size_t smem = (size_t)(2 * NV * TILE * 32 + NV * NC * SP + 3 * 6 * TILE) * sizeof(float);
-  auto kern = lookup_pipe_kernel<TILE, FV>;
+  const size_t smem = (size_t)(2 * NV * TILE * 32 + (DIRECT ? 0 : NV * NC * SP) + 3 * 6 * TILE) * sizeof(float);
+  auto kern = lookup_pipe_kernel<TILE, FV, DIRECT, HOLD>;
   static int per_sm = 0;
   if (per_sm == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -708,7 +725,7 @@ static int launch_pipe(const PLookupArgs& a, cudaStream_t st) {
   return finish_launch("sa_lookup_packed");
 }
 
-// 0: lookup_packed_kernel; 1: the pipelined kernel for dual lookups (SA_B200_LOOKUP_PIPE)
+// SA_B200_LOOKUP_PIPE: bit 0 = pipelined kernel for dual lookups, bit 1 = direct stores, bit 2 = no register hold
 static int pipe_mode() {
   static const int m = getenv("SA_B200_LOOKUP_PIPE") ? atoi(getenv("SA_B200_LOOKUP_PIPE")) : 0;
   return m;
@@ -810,8 +827,9 @@ extern "C" int sa_lookup_packed(const float* packed_a, const float* packed_b, in
   a.out[0] = out_a; a.out[1] = out_b;
   a.coords = coords; a.coords_bstride = coords_bstride;
   a.HW = H * W; a.W3 = W3; a.nblk = packed_blocks(W3); a.B = B;
-  if (packed_b && pipe_mode() && (a.HW & 3) == 0)
-    return pipe_mode() == 64 ? launch_pipe<64, -1>(a, (cudaStream_t)stream) : launch_pipe<32, -1>(a, (cudaStream_t)stream);
+  if (packed_b && (pipe_mode() & 1) && (a.HW & 3) == 0)
+    return (pipe_mode() & 2) ? launch_pipe<32, -1, true, true>(a, (cudaStream_t)stream)
+                             : launch_pipe<32, -1, false, true>(a, (cudaStream_t)stream);
   return packed_b ? launch_packed<2, -1>(a, B, (cudaStream_t)stream) : launch_packed<1, -1>(a, B, (cudaStream_t)stream);
 }
 
@@ -860,8 +878,15 @@ extern "C" int sa_lookup_packed_factored(const float* packed_a, const float* pac
   a.divisor = divisor; a.inv_divisor = (float)(1.0 / (double)divisor); a.post_scale = post_scale;
   if (packed_a) {
     a.packed[0] = packed_a; a.packed[1] = packed_normals_r; a.out[0] = out_a; a.out[1] = out_mono; a.B = B;
-    if (pipe_mode() && (a.HW & 3) == 0)
-      return pipe_mode() == 64 ? launch_pipe<64, 1>(a, (cudaStream_t)stream) : launch_pipe<32, 1>(a, (cudaStream_t)stream);
+    if ((pipe_mode() & 1) && (a.HW & 3) == 0) {
+      const cudaStream_t cs = (cudaStream_t)stream;
+      switch (pipe_mode() >> 1) {
+        case 0: return launch_pipe<32, 1, false, true>(a, cs);
+        case 1: return launch_pipe<32, 1, true, true>(a, cs);
+        case 2: return launch_pipe<32, 1, false, false>(a, cs);
+        default: return launch_pipe<32, 1, true, false>(a, cs);
+      }
+    }
     return launch_packed<2, -1, 1>(a, B, (cudaStream_t)stream);
   }
   a.packed[0] = packed_normals_r; a.out[0] = out_mono;

@@ -211,7 +211,6 @@ struct PLookupArgs {
   const float* nr;
   int H, Wimg;
   float divisor, inv_divisor, post_scale;
-  int B;  // batch (the pipelined kernel walks (b, tile) pairs itself)
   // factored mono volume (FV >= 0): packed[FV] holds the packed pyramid of the RIGHT NORMAL MAP's rows,
   // [(b*3 + c)*H + h][nblk][32]; nl / H / Wimg / divisor / inv_divisor / post_scale as above
 };
@@ -517,220 +516,6 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Pipelined form of the dual lookup (NV = 2; FV = 1: factored mono volume, FV = -1: two packed volumes).
-// lookup_packed_kernel is latency-bound: a CTA lives through coordinate load -> barrier -> line loads -> barrier
-// -> blend -> barrier -> stores, and with 2.7 waves of CTAs per launch nothing hides the two dependent DRAM round
-// trips.  Here a CTA is persistent and works on three tiles at once: while tile k is blended and stored, the lines
-// of tile k+1 are in flight (cp.async into the other stage buffer; the right-normal lines of the factored form are
-// held in registers across the blend) and the coordinates / left normals of tile k+2 are being loaded.  Two
-// barriers per tile; per-tile metadata (x, block, scaled normals) lives in three rotating shared-memory slots.
-// ---------------------------------------------------------------------------------------------
-// DIRECT: results go straight from registers to NCHW (one 128-byte line per warp store), no output tile and no
-// second barrier - 18.7 KB instead of 28.7 KB of shared memory per CTA.  HOLD: the factored form keeps the loaded
-// right-normal chunks in registers across the blend (false: combines them at once).
-template <int TILE, int FV, bool DIRECT, bool HOLD>
-__global__ void __launch_bounds__(2 * TILE, DIRECT ? 12 : 7) lookup_pipe_kernel(const PLookupArgs a) {
-  constexpr int NV = 2, THREADS = NV * TILE, NC = 36, SP = TILE + 4;
-  constexpr int STAGE = NV * TILE * 32;       // floats per stage buffer
-  constexpr int OUT = DIRECT ? 0 : NV * NC * SP;  // floats of the [channel][pixel] output tile
-  constexpr int META = 6 * TILE;              // floats per metadata slot: x, blk, float4 n
-  constexpr int UPS = THREADS / 8, SPV = 8 / NV;
-  static_assert(FV == 1 || FV == -1, "mono volume: factored or packed");
-  extern __shared__ __align__(16) float smem[];
-  float* const stage = smem;                  // [2][STAGE]
-  float* const tile = smem + 2 * STAGE;       // [OUT]
-  float* const meta = tile + OUT;             // [3][META]
-
-  const int tid = threadIdx.x;
-  const int p = tid % TILE, v = tid / TILE;
-  const int ch = tid & 7, u0 = tid >> 3;
-  const int tiles_x = (a.HW + TILE - 1) / TILE;
-  const long long ntiles = (long long)tiles_x * a.B;
-  const long long stride = gridDim.x;
-  const long long plane = (long long)a.H * a.Wimg;  // == HW
-  const int cplane = FV >= 0 ? a.H * a.nblk * 32 : 0;
-  const float kscale = a.post_scale * a.inv_divisor;
-
-  float rx = 0.f, rn0 = 0.f, rn1 = 0.f, rn2 = 0.f;  // coordinates / left normal of the tile two ahead (tid < TILE)
-
-  auto load_meta = [&](long long t) {
-    rx = rn0 = rn1 = rn2 = 0.f;
-    if (tid < TILE && t < ntiles) {
-      const int b = (int)(t / tiles_x);
-      const int hw = (int)(t - (long long)b * tiles_x) * TILE + tid;
-      if (hw < a.HW) {
-        rx = __ldg(a.coords + (long long)b * a.coords_bstride + hw);
-        if (FV >= 0) {
-          const float* nlp = a.nl + (long long)b * 3 * plane + hw;
-          rn0 = __ldg(nlp); rn1 = __ldg(nlp + plane); rn2 = __ldg(nlp + 2 * plane);
-        }
-      }
-    }
-  };
-  auto write_meta = [&](long long t, float* m) {  // from the registers filled by load_meta(t)
-    if (tid < TILE) {
-      int blk = -1, hw = 0;
-      if (t < ntiles) {
-        const int b = (int)(t / tiles_x);
-        hw = (int)(t - (long long)b * tiles_x) * TILE + tid;
-        if (hw < a.HW) {
-          const float fl = fminf(fmaxf(floorf(rx), -1.0e6f), 1.0e6f);
-          const int q = ((int)fl >> 3) - kQMin;
-          if (q >= 0 && q < a.nblk) blk = q;
-        }
-      }
-      m[tid] = rx;
-      reinterpret_cast<int*>(m)[TILE + tid] = blk;
-      if (FV >= 0) {
-        const float k = blk >= 0 ? kscale : 0.f;
-        const int off = blk >= 0 ? ((hw / a.Wimg) * a.nblk + blk) * 32 : 0;
-        reinterpret_cast<float4*>(m + 2 * TILE)[tid] = make_float4(rn0 * k, rn1 * k, rn2 * k, __int_as_float(off));
-      }
-    }
-  };
-  float4 r[SPV][3];  // factored form: this thread's chunks of the three right-normal lines of its SPV pixels
-  auto issue_lines = [&](long long t, const float* m, float* stg) {
-    const int b = (int)(t / tiles_x);
-    const int hw0 = (int)(t - (long long)b * tiles_x) * TILE;
-    const long long row0 = (long long)b * a.HW + hw0;
-    const int* s_blk = reinterpret_cast<const int*>(m) + TILE;
-#pragma unroll
-    for (int mm = 0; mm < SPV; ++mm) {
-      const int pm = u0 + mm * UPS;
-      const int blk = s_blk[pm];
-      const long long goff = blk >= 0 ? ((row0 + pm) * (long long)a.nblk + blk) * 32 + ch * 4 : -1;
-#pragma unroll
-      for (int vv = 0; vv < NV; ++vv) {
-        if (vv == FV) continue;
-        float* dst = stg + (vv * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2);
-        if (goff >= 0)
-          cp_async16(dst, (vv ? a.packed[1] : a.packed[0]) + goff);
-        else
-          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    if (FV >= 0) {
-      const float* rp = a.packed[FV >= 0 ? FV : 0] + (long long)b * 3 * cplane + ch * 4;
-      const float4* s_n = reinterpret_cast<const float4*>(m + 2 * TILE);
-#pragma unroll
-      for (int mm = 0; mm < SPV; ++mm) {
-        const int off = __float_as_int(s_n[u0 + mm * UPS].w);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) r[mm][c] = __ldg(reinterpret_cast<const float4*>(rp + (off + c * cplane)));
-      }
-    }
-  };
-  auto combine_lines = [&](const float* m, float* stg) {  // factored form: r -> the mono half of the stage buffer
-    const float4* s_n = reinterpret_cast<const float4*>(m + 2 * TILE);
-#pragma unroll
-    for (int mm = 0; mm < SPV; ++mm) {
-      const int pm = u0 + mm * UPS;
-      const float4 n = s_n[pm];
-      float4 o;
-      o.x = fmaf(n.z, r[mm][2].x, fmaf(n.y, r[mm][1].x, n.x * r[mm][0].x));
-      o.y = fmaf(n.z, r[mm][2].y, fmaf(n.y, r[mm][1].y, n.x * r[mm][0].y));
-      o.z = fmaf(n.z, r[mm][2].z, fmaf(n.y, r[mm][1].z, n.x * r[mm][0].z));
-      o.w = fmaf(n.z, r[mm][2].w, fmaf(n.y, r[mm][1].w, n.x * r[mm][0].w));
-      *reinterpret_cast<float4*>(stg + (FV * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2)) = o;
-    }
-  };
-
-  long long t = blockIdx.x;
-  if (t >= ntiles) return;
-  int s0 = 0, s1 = 1, s2 = 2;  // metadata slots of tiles k, k+1, k+2
-  // prologue: tile 0's metadata and lines, tile 1's coordinates
-  load_meta(t);
-  write_meta(t, meta + s0 * META);
-  load_meta(t + stride);
-  __syncthreads();
-  issue_lines(t, meta + s0 * META, stage);
-  if (FV >= 0) combine_lines(meta + s0 * META, stage);
-
-  for (int k = 0; t < ntiles; ++k, t += stride) {
-    const long long tn = t + stride;
-    float* const cur = stage + (k & 1) * STAGE;
-    float* const nxt = stage + ((k & 1) ^ 1) * STAGE;
-    write_meta(tn, meta + s1 * META);   // registers hold tile k+1's coordinates
-    load_meta(tn + stride);             // tile k+2's, in flight during this iteration
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();  // tile k's lines and tile k+1's metadata visible; the output tile is free again
-    if (tn < ntiles) {
-      issue_lines(tn, meta + s1 * META, nxt);
-      if (FV >= 0 && !HOLD) combine_lines(meta + s1 * META, nxt);
-    }
-
-    {  // blend tile k: thread (pixel p, volume v)
-      float l0[17], l1[13], l2[11], l3[10];
-      line_levels(cur + tid * 32, p, l0, l1, l2, l3);
-      if (DIRECT) {
-        const int b = (int)(t / tiles_x);
-        const int hw0 = (int)(t - (long long)b * tiles_x) * TILE;
-        float* const gout = (v ? a.out[1] : a.out[0]) + (long long)b * NC * a.HW + hw0 + p;
-        const long long cstride = a.HW;
-        const bool live = hw0 + p < a.HW;
-        blend_windows(l0, l1, l2, l3, meta[s0 * META + p], [&](int c, float val) {
-          if (live) st_stream_f32(gout + c * cstride, val);
-        });
-      } else {
-        blend_windows(l0, l1, l2, l3, meta[s0 * META + p], [&](int c, float val) { tile[(v * NC + c) * SP + p] = val; });
-      }
-    }
-    if (FV >= 0 && HOLD && tn < ntiles) combine_lines(meta + s1 * META, nxt);
-    if (!DIRECT) {
-      __syncthreads();
-      // [channel][pixel] tile -> NCHW (HW % 4 == 0: the launcher falls back to lookup_packed_kernel otherwise)
-      const int b = (int)(t / tiles_x);
-      const int hw0 = (int)(t - (long long)b * tiles_x) * TILE;
-      const int npx = min(TILE, a.HW - hw0);
-      constexpr int T4 = TILE / 4;
-      static_assert(THREADS == 4 * NV * T4 && NC % 4 == 0, "store mapping");
-      const int c0 = tid / T4, tt = (tid % T4) * 4;
-      if (tt < npx) {
-        const long long pix = (long long)b * NC * a.HW + hw0 + tt;
-        const long long cstride = (long long)a.HW;
-#pragma unroll
-        for (int kk = 0; kk < NC / 4; ++kk) {
-          const int c = c0 + 4 * NV * kk;          // 0 .. NV*NC-1
-          const int vv = c >= NC ? 1 : 0;
-          const int cc = c - vv * NC;
-          const float4 val = *reinterpret_cast<const float4*>(tile + c * SP + tt);
-          st_stream_v4((vv ? a.out[1] : a.out[0]) + pix + cc * cstride, val);
-        }
-      }
-    }
-    const int s = s0; s0 = s1; s1 = s2; s2 = s;
-  }
-}
-
-template <int TILE, int FV, bool DIRECT, bool HOLD>
-static int launch_pipe(const PLookupArgs& a, cudaStream_t st) {
-  constexpr int NV = 2, NC = 36, SP = TILE + 4;
-  const size_t smem = (size_t)(2 * NV * TILE * 32 + (DIRECT ? 0 : NV * NC * SP) + 3 * 6 * TILE) * sizeof(float);
-  auto kern = lookup_pipe_kernel<TILE, FV, DIRECT, HOLD>;
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) SA_FAIL((int)e, "sa_lookup_packed: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, NV * TILE, smem);
-    if (e != cudaSuccess || n < 1) SA_FAIL(e != cudaSuccess ? (int)e : SA_E_UNSUPPORTED, "sa_lookup_packed: occupancy query failed");
-    if (getenv("SA_B200_LOOKUP_PIPE_CTAS")) n = min(n, max(1, atoi(getenv("SA_B200_LOOKUP_PIPE_CTAS"))));
-    per_sm = n;
-  }
-  const long long ntiles = (long long)((a.HW + TILE - 1) / TILE) * a.B;
-  const long long cap = (long long)num_sms() * per_sm;
-  kern<<<(unsigned)(ntiles < cap ? ntiles : cap), NV * TILE, smem, st>>>(a);
-  return finish_launch("sa_lookup_packed");
-}
-
-// SA_B200_LOOKUP_PIPE: bit 0 = pipelined kernel for dual lookups, bit 1 = direct stores, bit 2 = no register hold
-static int pipe_mode() {
-  static const int m = getenv("SA_B200_LOOKUP_PIPE") ? atoi(getenv("SA_B200_LOOKUP_PIPE")) : 0;
-  return m;
-}
-
 template <int NV, int TILE, int OTF, int FV>
 static int launch_packed_t(const PLookupArgs& a, int B, cudaStream_t st) {
   constexpr int NC = 36, SP = TILE + 4;
@@ -826,10 +611,7 @@ extern "C" int sa_lookup_packed(const float* packed_a, const float* packed_b, in
   a.packed[0] = packed_a; a.packed[1] = packed_b;
   a.out[0] = out_a; a.out[1] = out_b;
   a.coords = coords; a.coords_bstride = coords_bstride;
-  a.HW = H * W; a.W3 = W3; a.nblk = packed_blocks(W3); a.B = B;
-  if (packed_b && (pipe_mode() & 1) && (a.HW & 3) == 0)
-    return (pipe_mode() & 2) ? launch_pipe<32, -1, true, true>(a, (cudaStream_t)stream)
-                             : launch_pipe<32, -1, false, true>(a, (cudaStream_t)stream);
+  a.HW = H * W; a.W3 = W3; a.nblk = packed_blocks(W3);
   return packed_b ? launch_packed<2, -1>(a, B, (cudaStream_t)stream) : launch_packed<1, -1>(a, B, (cudaStream_t)stream);
 }
 
@@ -877,16 +659,7 @@ extern "C" int sa_lookup_packed_factored(const float* packed_a, const float* pac
   a.nl = normals_l; a.H = H; a.Wimg = W;
   a.divisor = divisor; a.inv_divisor = (float)(1.0 / (double)divisor); a.post_scale = post_scale;
   if (packed_a) {
-    a.packed[0] = packed_a; a.packed[1] = packed_normals_r; a.out[0] = out_a; a.out[1] = out_mono; a.B = B;
-    if ((pipe_mode() & 1) && (a.HW & 3) == 0) {
-      const cudaStream_t cs = (cudaStream_t)stream;
-      switch (pipe_mode() >> 1) {
-        case 0: return launch_pipe<32, 1, false, true>(a, cs);
-        case 1: return launch_pipe<32, 1, true, true>(a, cs);
-        case 2: return launch_pipe<32, 1, false, false>(a, cs);
-        default: return launch_pipe<32, 1, true, false>(a, cs);
-      }
-    }
+    a.packed[0] = packed_a; a.packed[1] = packed_normals_r; a.out[0] = out_a; a.out[1] = out_mono;
     return launch_packed<2, -1, 1>(a, B, (cudaStream_t)stream);
   }
   a.packed[0] = packed_normals_r; a.out[0] = out_mono;

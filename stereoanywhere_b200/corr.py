@@ -127,23 +127,15 @@ class CorrBlockB200:
             _no_grad_check(truncate[0], truncate[1])  # the mask is detached in the reference (stereoanywhere.py:203)
         if fullcorr.dim() != 5 or fullcorr.shape[3] != 1:
             raise ValueError("fullcorr must be [B, H, W2, 1, W3] (reference corr.py:86)")
-        self.num_levels = num_levels
-        self.radius = radius
-        self.pad = list(pad)
         b, h, w2, _, w3 = fullcorr.shape
         if not fullcorr.is_contiguous():
             fullcorr = fullcorr.contiguous()
-        self._dlevels: Optional[List[torch.Tensor]] = None   # level-gradient accumulators (training only)
-        self._handle: Optional[torch.Tensor] = None
+        self._reset(num_levels, radius, pad, (b, h, w2, w3))
         grad_src = fullcorr if _needs_grad(fullcorr) else None
         if grad_src is not None:
             fullcorr = fullcorr.detach().float()
         self._src = fullcorr            # the tensor handed in (kept alive like the reference does)
         self._truncate = None if truncate is None else (truncate[0], truncate[1], float(truncate[2]))
-        self._shape = (b, h, w2, w3)
-        self._widths: List[int] = ops.level_widths(w3, num_levels)
-        self._levels: Optional[List[torch.Tensor]] = None
-        self._packed: Optional[torch.Tensor] = None
         rows = fullcorr.view(b * h * w2, w3)
         if self.layout == "packed" and ops.packable(num_levels, radius, w3, self.pad):
             # one 128-byte line per (pixel, volume) lookup; levels are materialised only on request
@@ -153,6 +145,22 @@ class CorrBlockB200:
             self._build_levels()
         if grad_src is not None:  # training: lookups go through autograd Functions
             self._handle = _PyramidFn.apply(grad_src.float() if grad_src.dtype != torch.float32 else grad_src, self)
+
+    def _reset(self, num_levels: int, radius: int, pad: Sequence[int], shape: Tuple[int, int, int, int]) -> None:
+        """Every field of a block, in its empty state; the constructors fill in what they build."""
+        self.num_levels, self.radius, self.pad = num_levels, radius, list(pad)
+        self._shape = shape                                   # (B, H, W2, W3)
+        self._widths: List[int] = ops.level_widths(shape[3], num_levels)
+        self._src: Optional[torch.Tensor] = None              # the un-truncated volume, if it exists
+        self._features: Optional[Tuple[torch.Tensor, torch.Tensor]] = None         # from_features: (fL, fR)
+        self._normals: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None   # from_normals: (nL, nR, gain)
+        self._truncate: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None
+        self._levels: Optional[List[torch.Tensor]] = None     # 16-byte-pitched levels (general layout)
+        self._packed: Optional[torch.Tensor] = None           # line-packed pyramid of the volume
+        self._packed_nr: Optional[torch.Tensor] = None        # mono_mode "factored": packed rows of the right normals
+        self._otf = False                                     # mono_mode "otf": lookups computed from the normals
+        self._dlevels: Optional[List[torch.Tensor]] = None    # level-gradient accumulators (training only)
+        self._handle: Optional[torch.Tensor] = None           # autograd tie to the volume (training only)
 
     #: "packed" (default; used whenever num_levels=4, radius=4, W3 % 8 == 0, pad=[0,0]) or "levels"
     layout = os.environ.get("SA_B200_LAYOUT", "packed")
@@ -164,22 +172,16 @@ class CorrBlockB200:
         `gain * corr(nL, nR)` is written straight from the normal maps; the volume itself is only formed
         if `fullcorr` / `corr_pyramid` are read.  Same values as `cls(cls.mono_corr(nL, nR))` - bit for bit with
         `mono_mode` "packed" / "otf", to fp32 rounding with the default "factored" (see `mono_mode`)."""
+        if cls.mono_mode not in ("factored", "packed", "otf"):
+            raise ValueError(f"CorrBlockB200.mono_mode must be 'factored', 'packed' or 'otf' (got {cls.mono_mode!r})")
         b, c, h, w2 = normals2.shape
         w3 = normals3.shape[3]
         if _needs_grad(normals2, normals3) or not (cls.layout == "packed" and ops.packable(num_levels, radius, w3, [0, 0])):
             return cls(cls.mono_corr(normals2, normals3, gain), num_levels=num_levels, radius=radius)
         self = cls.__new__(cls)
-        self.num_levels, self.radius, self.pad = num_levels, radius, [0, 0]
+        self._reset(num_levels, radius, (0, 0), (b, h, w2, w3))
         self._normals = (normals2.float(), normals3.float(), float(gain))
-        self._src = None
-        self._truncate = None
-        self._shape = (b, h, w2, w3)
-        self._widths = ops.level_widths(w3, num_levels)
-        self._levels = None
-        self._dlevels, self._handle = None, None
-        self._packed = None
         self._otf = cls.mono_mode == "otf"  # on-the-fly lookups (see mono_mode)
-        self._packed_nr = None
         if cls.mono_mode == "factored":     # packed pyramid of the right normal map's B*3*H rows (see mono_mode)
             self._packed_nr = _OPS.pack_pyramid(self._normals[1].contiguous().view(b * 3 * h, w3), None, None, 0.0)
         elif not self._otf:
@@ -199,7 +201,7 @@ class CorrBlockB200:
 
     def _ensure_packed(self) -> torch.Tensor:
         """The packed pyramid of this block (built on demand for on-the-fly / factored mono blocks)."""
-        if self._packed is None and (getattr(self, "_otf", False) or getattr(self, "_packed_nr", None) is not None):
+        if self._packed is None and (self._otf or self._packed_nr is not None):
             self._packed = _OPS.pack_pyramid_normals(self._normals[0], self._normals[1], self._normals[2])
             self._otf = False
             self._packed_nr = None
@@ -220,14 +222,9 @@ class CorrBlockB200:
                                              and ops.packable(num_levels, radius, w3, [0, 0]) and ops.corr_packable(c, w2, w3)):
             return cls(cls.corr(fmap2, fmap3), num_levels=num_levels, radius=radius, truncate=truncate)
         self = cls.__new__(cls)
-        self.num_levels, self.radius, self.pad = num_levels, radius, [0, 0]
+        self._reset(num_levels, radius, (0, 0), (b, h, w2, w3))
         self._features = (fmap2.float(), fmap3.float())
-        self._src = None
         self._truncate = None if truncate is None else (truncate[0], truncate[1], float(truncate[2]))
-        self._shape = (b, h, w2, w3)
-        self._widths = ops.level_widths(w3, num_levels)
-        self._levels = None
-        self._dlevels, self._handle = None, None
         t = self._truncate
         self._packed = _OPS.corr_pack(self._features[0], self._features[1], t[0] if t else None, t[1] if t else None,
                                       t[2] if t else 0.0)
@@ -236,7 +233,7 @@ class CorrBlockB200:
     def _source(self) -> torch.Tensor:
         """The un-truncated volume; formed on demand for blocks built by from_normals / from_features."""
         if self._src is None:
-            if getattr(self, "_features", None) is not None:
+            if self._features is not None:
                 self._src = CorrBlockB200.corr(*self._features)
             else:
                 self._src = CorrBlockB200.mono_corr(*self._normals)
@@ -268,9 +265,9 @@ class CorrBlockB200:
         return [lv[:, :w].unsqueeze(1).unsqueeze(1) for lv, w in zip(self._build_levels(), self._widths)]
 
     def _lookup_nograd(self, coords: torch.Tensor) -> torch.Tensor:
-        if getattr(self, "_otf", False):
+        if self._otf:
             return _OPS.lookup_normals(self._normals[0], self._normals[1], self._normals[2], coords)
-        if getattr(self, "_packed_nr", None) is not None:
+        if self._packed_nr is not None:
             return _OPS.lookup_factored(self._packed_nr, self._normals[0], self._normals[2], coords)
         if self._packed is not None:
             return _OPS.lookup_packed(self._packed, self._shape[3], coords)
@@ -321,11 +318,11 @@ class CorrBlockB200:
         _no_grad_check(coords)
         if torch.is_grad_enabled() and (block_a._handle is not None or block_b._handle is not None):
             return block_a(coords), block_b(coords)  # training: each lookup is its own autograd node
-        fact_b = getattr(block_b, "_packed_nr", None) is not None
-        otf_b = getattr(block_b, "_otf", False) or fact_b  # block_b holds no packed volume of its own
+        fact_b = block_b._packed_nr is not None
+        otf_b = block_b._otf or fact_b  # block_b holds no packed volume of its own
         if (block_a.radius != block_b.radius or block_a._widths != block_b._widths
-                or block_a.pad != [0, 0] or block_b.pad != [0, 0] or getattr(block_a, "_otf", False)
-                or getattr(block_a, "_packed_nr", None) is not None
+                or block_a.pad != [0, 0] or block_b.pad != [0, 0] or block_a._otf
+                or block_a._packed_nr is not None
                 or (block_a._packed is None) != (block_b._packed is None and not otf_b)):
             return block_a(coords), block_b(coords)
         dt = coords.dtype
@@ -334,7 +331,7 @@ class CorrBlockB200:
         if block_a._packed is not None and fact_b:
             oa, ob = _OPS.lookup_packed_factored2(block_a._packed, block_b._packed_nr, block_b._normals[0],
                                                   block_b._normals[2], coords)
-        elif block_a._packed is not None and getattr(block_b, "_otf", False):
+        elif block_a._packed is not None and block_b._otf:
             oa, ob = _OPS.lookup_packed_normals2(block_a._packed, block_b._normals[0], block_b._normals[1],
                                                  block_b._normals[2], coords)
         elif block_a._packed is not None:

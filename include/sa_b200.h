@@ -169,6 +169,12 @@ int sa_corr_pack_tf32(const float* fmap_l, const float* fmap_r, int B, int C, in
 int sa_lookup_packed_conv(const float* packed_a, const float* packed_b, int W3, const float* coords,
                           int64_t coords_bstride, const float* weight, const float* bias, float* out_a, float* out_b,
                           int B, int H, int W, void* stream);
+/* The same with the mono volume in factored form (packed_normals_r / normals_l / divisor / post_scale as in
+ * sa_lookup_packed_factored): the mono line of a pixel is combined from three right-normal lines while staging. */
+int sa_lookup_factored_conv(const float* packed_a, const float* packed_normals_r, const float* normals_l,
+                            float divisor, float post_scale, int W3, const float* coords, int64_t coords_bstride,
+                            const float* weight, const float* bias, float* out_a, float* out_mono, int B, int H, int W,
+                            void* stream);
 
 /* ---------------------------------------------------------------- soft-argmax / entropy reductions
  * The four reductions the model runs over the aggregated mono volume (stereoanywhere.py:174-177), two per

@@ -63,6 +63,8 @@ def _declare(lib):
     lib.sa_peer_reduce.argtypes = [vp, i, vp, vp, i64, vp]
     lib.sa_lookup_packed_conv.restype = i
     lib.sa_lookup_packed_conv.argtypes = [vp, vp, i, vp, i64, vp, vp, vp, vp, i, i, i, vp]
+    lib.sa_lookup_factored_conv.restype = i
+    lib.sa_lookup_factored_conv.argtypes = [vp, vp, vp, f, f, i, vp, i64, vp, vp, vp, vp, i, i, i, vp]
     lib.sa_truncate.restype = i
     lib.sa_truncate.argtypes = [vp, vp, vp, d, vp, i64, i, i, vp]
     lib.sa_masked_volume.restype = i
@@ -73,7 +75,7 @@ def _declare(lib):
 
 EXPORTS = [
     "sa_abi_version", "sa_last_error", "sa_corr_fp32", "sa_corr_tf32", "sa_pyramid", "sa_lookup", "sa_lookup2",
-    "sa_truncate", "sa_masked_volume", "sa_corrupt", "sa_packed_row_floats", "sa_pack_pyramid", "sa_pack_pyramid_normals", "sa_lookup_packed", "sa_lookup_packed_conv", "sa_corr_pack_tf32", "sa_peer_reduce", "sa_lookup_packed_normals", "sa_lookup_packed_factored", "sa_lookup_backward", "sa_pyramid_backward", "sa_volume_softargmax", "sa_volume_entropy_conf",
+    "sa_truncate", "sa_masked_volume", "sa_corrupt", "sa_packed_row_floats", "sa_pack_pyramid", "sa_pack_pyramid_normals", "sa_lookup_packed", "sa_lookup_packed_conv", "sa_lookup_factored_conv", "sa_corr_pack_tf32", "sa_peer_reduce", "sa_lookup_packed_normals", "sa_lookup_packed_factored", "sa_lookup_backward", "sa_pyramid_backward", "sa_volume_softargmax", "sa_volume_entropy_conf",
 ]
 
 

@@ -349,9 +349,13 @@ def lookup_pair_convc1(block_a: CorrBlockB200, block_b: CorrBlockB200, coords: t
     Falls back to two lookups + torch convolutions when the blocks are not in the packed layout."""
     _no_grad_check(coords, weight, bias)
     block_a._ensure_packed()
+    convc1 = weight.shape[0] == 64 and weight.shape[1] == 36
+    if block_b._packed_nr is not None and block_a._packed is not None and block_a._shape == block_b._shape and convc1:
+        # factored mono block: its line is combined from the packed right normals inside the kernel
+        return _OPS.lookup_factored_conv(block_a._packed, block_b._packed_nr, block_b._normals[0], block_b._normals[2],
+                                         coords.float(), weight.float(), bias.float())
     block_b._ensure_packed()  # an on-the-fly mono block is packed on first use here
-    if (block_a._packed is None or block_b._packed is None or block_a._shape != block_b._shape
-            or weight.shape[0] != 64 or weight.shape[1] != 36):
+    if (block_a._packed is None or block_b._packed is None or block_a._shape != block_b._shape or not convc1):
         sa_, sb_ = CorrBlockB200.lookup_pair(block_a, block_b, coords)
         conv = torch.nn.functional.conv2d
         return torch.relu(conv(sa_, weight, bias)), torch.relu(conv(sb_, weight, bias))

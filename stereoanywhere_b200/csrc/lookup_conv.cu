@@ -32,6 +32,11 @@ struct LcArgs {
   const float* bias;    // [64]
   long long coords_bstride;
   int HW, nblk, B;
+  // FACT: packed[1] is the packed pyramid of the right normal map's rows ([(b*3 + c)*H + h][nblk][32], see
+  // csrc/packed.cu, factored mono volume), nl the left normals [B,3,H,Wimg], kscale = post_scale / divisor
+  const float* nl;
+  int H, Wimg;
+  float kscale;
 };
 
 __device__ __forceinline__ void lc_cp_async16(void* smem_dst, const void* gsrc) {
@@ -56,7 +61,8 @@ __device__ __forceinline__ uint32_t a_off(int p, int k) {
   return off ^ (((off >> 7) & 3) << 5);
 }
 
-__global__ void __launch_bounds__(2 * kLcTile) lookup_conv_kernel(const LcArgs a) {
+template <bool FACT>
+__global__ void __launch_bounds__(2 * kLcTile, 4) lookup_conv_kernel(const LcArgs a) {
   constexpr int TILE = kLcTile, THREADS = 2 * kLcTile;
   extern __shared__ uint8_t lc_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lc_raw) + 1023) & ~uintptr_t(1023));
@@ -115,17 +121,30 @@ __global__ void __launch_bounds__(2 * kLcTile) lookup_conv_kernel(const LcArgs a
   const int npx = min(TILE, a.HW - hw0);
   const long long row0 = (long long)b * a.HW + hw0;
 
+  // FACT: {k n0, k n1, k n2, line offset} per pixel, in the 8 KB of the A operands that the line staging leaves free
+  float4* s_n = reinterpret_cast<float4*>(sA + 2 * TILE * 128);
   if (tid < TILE) {
     float x = 0.f;
     int blk = -1;
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f;
     if (tid < npx) {
       x = __ldg(a.coords + (long long)b * a.coords_bstride + hw0 + tid);
+      if (FACT) {
+        const long long plane = (long long)a.H * a.Wimg;
+        const float* nlp = a.nl + (long long)b * 3 * plane + hw0 + tid;
+        n0 = __ldg(nlp); n1 = __ldg(nlp + plane); n2 = __ldg(nlp + 2 * plane);
+      }
       const float fl = fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
       const int q = ((int)fl >> 3) + 5;  // blocks start at q = -5 (csrc/packed.cu)
       if (q >= 0 && q < a.nblk) blk = q;
     }
     s_x[tid] = x;
     s_blk[tid] = blk;
+    if (FACT) {  // a pixel without a line reads line 0 with zero coefficients
+      const float k = blk >= 0 ? a.kscale : 0.f;
+      const int off = blk >= 0 ? (((hw0 + tid) / a.Wimg) * a.nblk + blk) * 32 : 0;
+      s_n[tid] = make_float4(n0 * k, n1 * k, n2 * k, __int_as_float(off));
+    }
   }
   __syncthreads();
 
@@ -144,6 +163,7 @@ __global__ void __launch_bounds__(2 * kLcTile) lookup_conv_kernel(const LcArgs a
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
       const int v = n / SPV, m = n % SPV;
+      if (FACT && v == 1) continue;
       const int pm = u0 + m * UPS;
       float* dst = stage + (v * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2);
       if (goff[m] >= 0)
@@ -151,8 +171,30 @@ __global__ void __launch_bounds__(2 * kLcTile) lookup_conv_kernel(const LcArgs a
       else
         *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (FACT) {  // the mono line = three right-normal lines combined with the pixel's scaled left normal
+      const int cplane = a.H * a.nblk * 32;
+      const float* rp = a.packed[1] + (long long)b * 3 * cplane + ch * 4;
+      float4 r[SPV][3], nn[SPV];
+#pragma unroll
+      for (int m = 0; m < SPV; ++m) {
+        nn[m] = s_n[u0 + m * UPS];
+        const int off = __float_as_int(nn[m].w);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) r[m][c] = __ldg(reinterpret_cast<const float4*>(rp + (off + c * cplane)));
+      }
+#pragma unroll
+      for (int m = 0; m < SPV; ++m) {
+        const int pm = u0 + m * UPS;
+        float4 o;
+        o.x = fmaf(nn[m].z, r[m][2].x, fmaf(nn[m].y, r[m][1].x, nn[m].x * r[m][0].x));
+        o.y = fmaf(nn[m].z, r[m][2].y, fmaf(nn[m].y, r[m][1].y, nn[m].x * r[m][0].y));
+        o.z = fmaf(nn[m].z, r[m][2].z, fmaf(nn[m].y, r[m][1].z, nn[m].x * r[m][0].z));
+        o.w = fmaf(nn[m].z, r[m][2].w, fmaf(nn[m].y, r[m][1].w, nn[m].x * r[m][0].w));
+        *reinterpret_cast<float4*>(stage + (TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2)) = o;
+      }
+    }
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
@@ -285,6 +327,20 @@ __global__ void __launch_bounds__(2 * kLcTile) lookup_conv_kernel(const LcArgs a
 
 }  // namespace sa
 
+namespace sa {
+template <bool FACT>
+static int launch_lookup_conv(const LcArgs& a, cudaStream_t st, const char* what) {
+  const size_t smem = 1024 + 2 * kLcABytes + kLcBBytes + (kLcN + 2 * kLcTile) * sizeof(float) + 32;
+  cudaError_t e = cudaFuncSetAttribute(lookup_conv_kernel<FACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) SA_FAIL((int)e, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+  const long long ntiles = (long long)((a.HW + kLcTile - 1) / kLcTile) * a.B;
+  const long long cap = (long long)num_sms() * 4;  // 4 CTAs per SM fit (shared memory, 128 TMEM columns each)
+  const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
+  lookup_conv_kernel<FACT><<<grid, 2 * kLcTile, smem, st>>>(a);
+  return finish_launch(what);
+}
+}  // namespace sa
+
 extern "C" int sa_lookup_packed_conv(const float* packed_a, const float* packed_b, int W3, const float* coords,
                                      int64_t coords_bstride, const float* weight, const float* bias, float* out_a,
                                      float* out_b, int B, int H, int W, void* stream) {
@@ -303,12 +359,30 @@ extern "C" int sa_lookup_packed_conv(const float* packed_a, const float* packed_
   a.HW = H * W;
   a.nblk = W3 / 8 + 9;
   a.B = B;
-  const size_t smem = 1024 + 2 * kLcABytes + kLcBBytes + (kLcN + 2 * kLcTile) * sizeof(float) + 32;
-  cudaError_t e = cudaFuncSetAttribute(lookup_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) SA_FAIL((int)e, "sa_lookup_packed_conv: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const long long ntiles = (long long)((a.HW + kLcTile - 1) / kLcTile) * B;
-  const long long cap = (long long)num_sms() * 4;  // 4 CTAs per SM fit (shared memory, 128 TMEM columns each)
-  const unsigned grid = (unsigned)(ntiles < cap ? ntiles : cap);
-  lookup_conv_kernel<<<grid, 2 * kLcTile, smem, (cudaStream_t)stream>>>(a);
-  return finish_launch("sa_lookup_packed_conv");
+  return launch_lookup_conv<false>(a, (cudaStream_t)stream, "sa_lookup_packed_conv");
+}
+
+extern "C" int sa_lookup_factored_conv(const float* packed_a, const float* packed_normals_r, const float* normals_l,
+                                       float divisor, float post_scale, int W3, const float* coords,
+                                       int64_t coords_bstride, const float* weight, const float* bias, float* out_a,
+                                       float* out_mono, int B, int H, int W, void* stream) {
+  using namespace sa;
+  SA_REQUIRE(packed_a && packed_normals_r && normals_l && coords && weight && bias && out_a && out_mono, SA_E_INVALID,
+             "sa_lookup_factored_conv: null pointer");
+  SA_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 31) && divisor != 0.f, SA_E_INVALID,
+             "sa_lookup_factored_conv: bad sizes");
+  SA_REQUIRE(W3 >= 8 && W3 % 8 == 0, SA_E_UNSUPPORTED, "sa_lookup_factored_conv: W3 must be a multiple of 8");
+  SA_REQUIRE(aligned16(packed_a) && aligned16(packed_normals_r), SA_E_ALIGN,
+             "sa_lookup_factored_conv: packed arrays must be 16-byte aligned");
+  LcArgs a = {};
+  a.packed[0] = packed_a; a.packed[1] = packed_normals_r;
+  a.out[0] = out_a; a.out[1] = out_mono;
+  a.coords = coords; a.coords_bstride = coords_bstride;
+  a.weight = weight; a.bias = bias;
+  a.HW = H * W;
+  a.nblk = W3 / 8 + 9;
+  a.B = B;
+  a.nl = normals_l; a.H = H; a.Wimg = W;
+  a.kscale = post_scale * (float)(1.0 / (double)divisor);
+  return launch_lookup_conv<true>(a, (cudaStream_t)stream, "sa_lookup_factored_conv");
 }

@@ -479,6 +479,35 @@ def _lookup_packed_conv(packed_a: torch.Tensor, packed_b: torch.Tensor, w3: int,
     return out_a, out_b
 
 
+def _lookup_factored_conv(packed_a: torch.Tensor, packed_nr: torch.Tensor, normals_l: torch.Tensor, post_scale: float,
+                          coords: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor):
+    """`_lookup_packed_conv` with the mono volume in factored form (packed right normals + left normals)."""
+    coords, b, h, w = _coords_view(coords)
+    for t, n in ((packed_a, "packed_a"), (packed_nr, "packed right normals"), (normals_l, "normals_l"), (weight, "weight"),
+                 (bias, "bias")):
+        _cuda_f32(t, n)
+    _req(normals_l.shape == (b, 3, h, w), "normals_l must be [B,3,H,W] matching coords")
+    _req(packed_nr.dim() == 2 and packed_nr.shape[0] == b * 3 * h and packed_nr.is_contiguous(),
+         "packed right normals must be [B*3*H, row floats]")
+    w3 = (packed_nr.shape[1] // 32 - 9) * 8
+    _req(w3 >= 8 and packed_row_floats(w3) == packed_nr.shape[1], "bad packed row size")
+    _req(packed_a.shape == (b * h * w, packed_row_floats(w3)), "coords do not match the packed volume")
+    _req(weight.numel() == 64 * 36 and bias.numel() == 64, "convc1 must be Conv2d(36, 64, 1): weight [64,36,1,1], bias [64]")
+    weight = weight.reshape(64, 36).contiguous()
+    bias = bias.contiguous()
+    normals_l = normals_l.contiguous()
+    out_a = torch.empty((b, 64, h, w), dtype=torch.float32, device=coords.device)
+    out_m = torch.empty_like(out_a)
+    lib = _lib.load()
+    divisor = float(torch.sqrt(torch.tensor(3)))
+    with _on(coords.device):
+        rc = lib.sa_lookup_factored_conv(packed_a.data_ptr(), packed_nr.data_ptr(), normals_l.data_ptr(), divisor,
+                                         float(post_scale), w3, coords.data_ptr(), coords.stride(0), weight.data_ptr(),
+                                         bias.data_ptr(), out_a.data_ptr(), out_m.data_ptr(), b, h, w, _stream_ptr(coords))
+    _lib.check(rc, "sa_lookup_factored_conv")
+    return out_a, out_m
+
+
 def _lookup_packed1(packed: torch.Tensor, w3: int, coords: torch.Tensor) -> torch.Tensor:
     return _lookup_packed(packed, None, w3, coords)[0]
 
@@ -585,6 +614,7 @@ _LIBDEF.define("lookup_packed_factored2(Tensor packed_a, Tensor packed_nr, Tenso
 _LIBDEF.define("lookup_packed(Tensor packed, int w3, Tensor coords) -> Tensor")
 _LIBDEF.define("lookup_packed2(Tensor packed_a, Tensor packed_b, int w3, Tensor coords) -> (Tensor, Tensor)")
 _LIBDEF.define("lookup_packed_conv(Tensor packed_a, Tensor packed_b, int w3, Tensor coords, Tensor weight, Tensor bias) -> (Tensor, Tensor)")
+_LIBDEF.define("lookup_factored_conv(Tensor packed_a, Tensor packed_nr, Tensor normals_l, float post_scale, Tensor coords, Tensor weight, Tensor bias) -> (Tensor, Tensor)")
 _LIBDEF.define("truncate(Tensor? vol, Tensor disp, Tensor conf, float gain) -> Tensor")
 _LIBDEF.define("masked_volume(Tensor? vol, Tensor? normals_l, Tensor? normals_r, float post_scale, Tensor mde_l, Tensor mde_r, int n_bins) -> Tensor")
 _LIBDEF.define("corrupt(Tensor vol, Tensor bin_mask, int mode, int shift, Tensor? noise, float gauss_k) -> Tensor")
@@ -605,9 +635,10 @@ _LIBDEF.impl("lookup_packed_factored2", _lookup_packed_factored2, "CUDA")
 _LIBDEF.impl("lookup_packed", _lookup_packed1, "CUDA")
 _LIBDEF.impl("lookup_packed2", _lookup_packed2, "CUDA")
 _LIBDEF.impl("lookup_packed_conv", _lookup_packed_conv, "CUDA")
+_LIBDEF.impl("lookup_factored_conv", _lookup_factored_conv, "CUDA")
 _LIBDEF.impl("truncate", _truncate, "CUDA")
 _LIBDEF.impl("masked_volume", _masked_volume, "CUDA")
 _LIBDEF.impl("corrupt", _corrupt, "CUDA")
 
-OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "corr_pack", "lookup_normals", "lookup_packed_normals2", "lookup_factored", "lookup_packed_factored2", "volume_softargmax", "volume_entropy_conf", "lookup_packed", "lookup_packed2", "lookup_packed_conv",
+OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "corr_pack", "lookup_normals", "lookup_packed_normals2", "lookup_factored", "lookup_packed_factored2", "volume_softargmax", "volume_entropy_conf", "lookup_packed", "lookup_packed2", "lookup_packed_conv", "lookup_factored_conv",
             "truncate", "masked_volume", "corrupt"]

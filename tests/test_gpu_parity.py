@@ -754,14 +754,19 @@ def test_mono_lookup_factored(sa, shape):
         s1, m1 = B.lookup_pair(stereo, fc, coords)
         s2, m2 = B.lookup_pair(stereo, pk, coords)
         assert torch.equal(m1, got) and torch.equal(s1, s2), kind
-    # consumers that need the packed volume get it on demand; the reference attributes still work
-    assert torch.equal(fc.fullcorr, pk.fullcorr)
+    assert torch.equal(fc.fullcorr, pk.fullcorr)  # the reference attributes still work
     w = (torch.randn(64, 36, 1, 1, generator=gen) / 6).to(DEV)
-    bias = torch.zeros(64, device=DEV)
+    # lookup + convc1 takes the factored block as it is (sa_lookup_factored_conv): the stereo half is
+    # the packed kernel's bit for bit, the mono half sees taps that differ by fp32 rounding before the tf32 product
+    bias = (torch.randn(64, generator=gen) / 4).to(DEV)
     fa, fb = sa.lookup_pair_convc1(stereo, fc, coords, w, bias)
     ga, gb = sa.lookup_pair_convc1(stereo, pk, coords, w, bias)
-    assert torch.equal(fb, gb) and torch.equal(fa, ga)
-    assert fc._packed is not None and fc._packed_nr is None
+    assert fc._packed is None and fc._packed_nr is not None
+    assert torch.equal(fa, ga) and normwise(fb, gb) < 1e-3
+    conv = torch.relu(torch.nn.functional.conv2d(pk(coords).double(), w.double(), bias.double()))
+    assert normwise(fb, conv) < 1e-3
+    # consumers that need the packed volume get it on demand
+    assert torch.equal(fc._ensure_packed(), pk._packed) and fc._packed_nr is None
 
 
 def test_more_than_2_31_packed_floats(sa):

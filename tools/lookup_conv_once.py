@@ -33,3 +33,12 @@ tf, of = timeit(fused)
 tu, ou = timeit(unfused)
 err = float((of[0] - ou[0]).abs().max() / ou[0].abs().max())
 print(f"fused lookup+convc1: {tf:.1f} us   lookup_pair + 2x(cuDNN conv1x1 + relu): {tu:.1f} us   normwise diff {err:.2e}")
+# the mono block in factored form (from_normals, default mode): sa_lookup_factored_conv
+nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w, device=dev, generator=g), dim=1)
+nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w, device=dev, generator=g), dim=1)
+del bb
+bb = B.from_normals(nl, nr)
+tf, of = timeit(fused)
+tu, ou = timeit(unfused)
+err = float((of[1] - ou[1]).abs().max() / ou[1].abs().max())
+print(f"factored mono ({B.mono_mode}): fused {tf:.1f} us   unfused {tu:.1f} us   normwise diff (mono) {err:.2e}")

@@ -569,6 +569,11 @@ def run_tiled(args):
     # closing event of the timed region.  The weight plane sum(w) depends on the geometry only: rank 0 forms
     # it once (tiling.weight_sum) instead of reducing it every step.
     stitcher = None
+    istitch = None
+    if dist is not None and args.stitch == "image" and tiling.plan_images(args.images, world) is not None:
+        # tiles sharded by image: only the ranks that share an image reduce its plane, leaders send finished planes
+        istitch = tiling.ImageStitcher(args.images, H, W, work, dev)
+        mine = istitch.units(work)
     if dist is not None and args.stitch == "peer":
         # reduce + normalise + gather over NVLink peer memory in one kernel per rank (tiling.PeerStitcher) instead of
         # an SM-resident NCCL reduce next to the persistent GEMM kernels; falls back to NCCL if symmetric memory
@@ -579,8 +584,8 @@ def run_tiled(args):
             if rank == 0:
                 print(f"[bench] peer stitch unavailable ({type(e).__name__}: {e}); using NCCL reduce", file=sys.stderr)
             stitcher = None
-    acc_bufs = [torch.empty(args.images, H, W, device=dev) for _ in range(2)] if stitcher is None else None
-    den = torch.clamp(tiling.weight_sum(H, W, work, device=dev), min=1e-4) if rank == 0 else None
+    acc_bufs = [torch.empty(args.images, H, W, device=dev) for _ in range(2)] if stitcher is None and istitch is None else None
+    den = torch.clamp(tiling.weight_sum(H, W, work, device=dev), min=1e-4) if rank == 0 and istitch is None else None
     pending = [None, None]
     step_no = [0]
 
@@ -596,7 +601,9 @@ def run_tiled(args):
     def step():
         i = step_no[0] & 1
         step_no[0] += 1
-        if stitcher is not None:
+        if istitch is not None:
+            accs = istitch.buffer(i)
+        elif stitcher is not None:
             accs = stitcher.buffer(i)
         else:
             finish(i)
@@ -610,13 +617,17 @@ def run_tiled(args):
             key = (y1 - y0, x1 - x0, mult)
             if key not in weights:
                 weights[key] = tiling.blend_weight(key[0], key[1], device=dev) * float(mult)
-            accs[img, y0:y1, x0:x1].addcmul_(full[0, 0], weights[key])
-        if stitcher is not None:
+            accs[img if istitch is None else istitch.slot[img], y0:y1, x0:x1].addcmul_(full[0, 0], weights[key])
+        if istitch is not None:
+            istitch.launch(i)
+        elif stitcher is not None:
             stitcher.reduce_to(i, 0)
         else:
             pending[i] = dist.reduce(accs, dst=0, op=dist.ReduceOp.SUM, async_op=True) if dist is not None else "local"
 
     def drain():
+        if istitch is not None:
+            return [istitch.drain()]
         if stitcher is not None:
             stitcher.drain()
             return [stitcher.result()]
@@ -653,7 +664,10 @@ def run_tiled(args):
             "data": "synthetic", "config": {"workload": args.workload, "images_per_step": args.images, "tile_preset": args.tile_preset,
                                            "distinct_tiles_per_image": len(work), "tiles_this_rank": len(mine),
                                            "cuda_graph": bool(args.graph),
-                                           "parallelism": (f"tiles sharded x{world}, stitch = reduce + normalise + gather over NVLink peer memory, one "
+                                           "parallelism": (f"tiles sharded x{world} image by image ({len(istitch.ranks_of[0])} rank(s) per image): "
+                                                           f"async sub-group reduce of one [H,W] plane, leaders normalise and send "
+                                                           f"the finished planes to rank 0") if istitch is not None else
+                                                          (f"tiles sharded x{world}, stitch = reduce + normalise + gather over NVLink peer memory, one "
                                                            f"kernel per rank (sa_peer_reduce), side stream") if stitcher is not None else
                                                           f"tiles sharded x{world}, one async NCCL reduce(sum) of [images,H,W] per step"},
         })
@@ -766,9 +780,11 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + ["c4_middlebury_1984x2872_tiled"])
     ap.add_argument("--tile-preset", default="middlebury", help="reference tile preset for the tiled workload")
     ap.add_argument("--images", type=int, default=4, help="full-resolution pairs per step of the tiled workload")
-    ap.add_argument("--stitch", default="nccl", choices=["peer", "nccl"],
-                    help="tiled workload, N > 1: async NCCL reduce (default, measured faster) or reduce + normalise + gather over "
-                         "NVLink peer memory (tiling.PeerStitcher / sa_peer_reduce)")
+    ap.add_argument("--stitch", default="nccl", choices=["image", "peer", "nccl"],
+                    help="tiled workload, N > 1: 'nccl' = one async global reduce of [images,H,W] (default, measured fastest); "
+                         "'image' = tiles sharded image by image, sub-group reduce of single planes + send of the finished "
+                         "planes (tiling.ImageStitcher; falls back to 'nccl' when images and ranks do not divide); 'peer' = "
+                         "reduce + normalise + gather over NVLink peer memory (tiling.PeerStitcher / sa_peer_reduce)")
     ap.add_argument("--variant", default="fused", choices=["fused", "protocol"],
                     help="fused: truncate= / mono_corr / lookup_pair entry points; protocol: the reference's exact call sequence")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"], help="stereo correlation kernel")

@@ -193,6 +193,115 @@ def gather_batch(local: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat(parts, dim=0)
 
 
+def plan_images(images: int, world: int):
+    """How `images` full-resolution images are spread over `world` ranks so that a rank only ever holds - and
+    communicates - the planes of its own images.  Returns `ranks_of[j]` (the ranks that share image j; the first
+    one is its leader), or None when neither number divides the other (then every rank takes tiles of every image
+    and the stitch is one global reduce)."""
+    if world >= images and world % images == 0:
+        per = world // images
+        return [list(range(j * per, (j + 1) * per)) for j in range(images)]
+    if images % world == 0:
+        per = images // world
+        return [[j // per] for j in range(images)]
+    return None
+
+
+class ImageStitcher:
+    """Stitch of a tile-sharded step over several images with the least data on the wire (config 4, N ranks).
+
+    A global `reduce(sum)` of the `[images, H, W]` accumulator makes every rank push the whole 91 MB (four
+    Middlebury images) through the ring although it only touched its own tiles.  Here the tiles are sharded BY IMAGE
+    (`plan_images`): the ranks that share an image reduce just that `[H, W]` plane among themselves (a sub-group
+    collective; nothing at all when an image belongs to one rank), its leader divides by the weight plane (geometry
+    only, formed locally) and sends the finished plane to the gathering rank.  Both phases are asynchronous and
+    double-buffered: the sub-group reduce of step k is launched after step k's tiles, its normalise + send when step
+    k+1's tiles have been issued, and everything of parity i is waited for when that buffer comes round again.
+    """
+
+    def __init__(self, images: int, height: int, width: int, work, device, group=None, dst: int = 0):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.dst = dst
+        self.ranks_of = plan_images(images, self.world)
+        if self.ranks_of is None:
+            raise ValueError(f"{images} images cannot be spread over {self.world} ranks image by image")
+        self.images = images
+        self.my_images = [j for j, rk in enumerate(self.ranks_of) if self.rank in rk]
+        self.slot = {j: k for k, j in enumerate(self.my_images)}      # image -> index in my accumulator
+        self.shared = len(self.ranks_of[0]) > 1
+        # every rank creates every sub-group, in the same order (torch.distributed requirement)
+        self.groups = [dist.new_group(rk) if self.shared else None for rk in self.ranks_of]
+        self.lead = [j for j in self.my_images if self.ranks_of[j][0] == self.rank]   # images I finish and send
+        n = max(1, len(self.my_images))
+        self.acc = [torch.zeros(n, height, width, dtype=torch.float32, device=device) for _ in range(2)]
+        self.den = torch.clamp(weight_sum(height, width, work, device=device), min=1e-4) if self.lead else None
+        self.norm = [torch.empty(len(self.lead), height, width, dtype=torch.float32, device=device) for _ in range(2)] \
+            if self.lead else None
+        self.out = torch.zeros(images, height, width, dtype=torch.float32, device=device) if self.rank == dst else None
+        self._reduce = [[], []]   # outstanding sub-group reduces of parity i
+        self._p2p = [[], []]      # outstanding sends / receives of parity i
+        self._stage = [0, 0]      # 0 idle, 1 reduce launched, 2 normalise + send launched
+
+    def units(self, work) -> List:
+        """This rank's (image, tile, multiplicity) units: the tiles of its images, round-robin inside an image."""
+        mine = []
+        for j in self.my_images:
+            rk = self.ranks_of[j]
+            mine += [(j, t, m) for i, (t, m) in enumerate(work) if i % len(rk) == rk.index(self.rank)]
+        return mine
+
+    def buffer(self, i: int) -> torch.Tensor:
+        """Accumulator `[my images, H, W]` of parity i (index with `slot[image]`), free to be overwritten."""
+        self._finish(i)
+        return self.acc[i]
+
+    def launch(self, i: int) -> None:
+        """Step k's tiles have been accumulated into buffer i: start its reduce, and move step k-1 one phase on."""
+        if self.shared:
+            for j in self.my_images:
+                k = self.slot[j]
+                self._reduce[i].append(self.dist.reduce(self.acc[i][k], dst=self.ranks_of[j][0], op=self.dist.ReduceOp.SUM,
+                                                        group=self.groups[j], async_op=True))
+        self._stage[i] = 1
+        if self._stage[i ^ 1] == 1:
+            self._send(i ^ 1)
+
+    def _send(self, i: int) -> None:
+        for w in self._reduce[i]:
+            w.wait()
+        self._reduce[i] = []
+        for n, j in enumerate(self.lead):
+            torch.div(self.acc[i][self.slot[j]], self.den, out=self.norm[i][n])
+            if self.rank == self.dst:
+                self.out[j].copy_(self.norm[i][n])
+            else:
+                self._p2p[i].append(self.dist.isend(self.norm[i][n], dst=self.dst, group=self.group))
+        if self.rank == self.dst:
+            for j, rk in enumerate(self.ranks_of):
+                if rk[0] != self.dst:
+                    self._p2p[i].append(self.dist.irecv(self.out[j], src=rk[0], group=self.group))
+        self._stage[i] = 2
+
+    def _finish(self, i: int) -> None:
+        if self._stage[i] == 1:
+            self._send(i)
+        for w in self._p2p[i]:
+            w.wait()
+        self._p2p[i] = []
+        self._stage[i] = 0
+
+    def drain(self) -> Optional[torch.Tensor]:
+        """Complete everything outstanding (oldest step first); the stitched `[images, H, W]` on the gathering rank."""
+        order = (0, 1) if self._stage[0] >= self._stage[1] else (1, 0)
+        for i in order:
+            self._finish(i)
+        return self.out
+
+
 class PeerStitcher:
     """Stitch of a tile-sharded step over NVLink peer memory instead of an NCCL reduce (config 4).
 

@@ -92,3 +92,24 @@ def test_packed_row_floats_matches_library():
     lib = _lib.load()
     for w in (8, 40, 128, 312, 768, 1024):
         assert ops.packed_row_floats(w) == int(lib.sa_packed_row_floats(w))
+
+
+def test_sass_uses_the_blackwell_units():
+    """The shipped library is sm_100a code that really issues tcgen05 MMAs out of TMEM and TMA loads / stores
+    (SASS mnemonics of /opt/skills/guides/B200_PROFILING.md): UTCHMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG /
+    UTMASTG (cp.async.bulk.tensor), LDGSTS (cp.async) - not a recompiled mma.sync / SIMT fallback."""
+    import shutil
+    import subprocess
+
+    import stereoanywhere_b200._lib as L
+
+    L.load()
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([tool, "-sass", L.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    archs = set(re.findall(r"arch = (sm_\w+)", sass))
+    assert archs == {"sm_100a"}, archs
+    for mnemonic, least in (("UTCHMMA", 8), ("LDTM", 3), ("UTMALDG", 8), ("UTMASTG", 4), ("LDGSTS", 8)):
+        assert sass.count(mnemonic) >= least, f"{mnemonic}: {sass.count(mnemonic)} occurrences"
+    assert "HMMA.16816" not in sass and "WGMMA" not in sass

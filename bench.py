@@ -438,6 +438,11 @@ def run_gpu(args):
                 "traffic": TRAFFIC_BYTES.get((args.workload, args.variant, "packed" if args.mono == "aggregated" else args.mono)), "peak_source": peak_src,
                 "algorithmic_bytes_per_pixel": alg_px,
                 "algorithmic_bytes_per_launch": alg, "launch_us": round(lk_launch_ms * 1e3, 2),
+                # SURVEY 8d counts 612 B/px for the dual lookup (both volumes' windows read from memory); the factored
+                # and on-the-fly forms do not read the mono windows, `achieved` above uses their own smaller figure
+                "survey_8d_definition": {"bytes_per_pixel": 612 if args.variant == "fused" else 308,
+                                         "gbs": round((612 if args.variant == "fused" else 308) * p / (lk_launch_ms * 1e-3) / 1e9, 1),
+                                         "frac": round((612 if args.variant == "fused" else 308) * p / (lk_launch_ms * 1e-3) / 1e9 / peak, 4)},
                 "path_algorithmic_gbs": round(path_bytes(b, c, h, w) / (ms_step * 1e-3) / 1e9, 1)}
         kernels = None
         if breakdown is not None:

@@ -113,3 +113,23 @@ def test_sass_uses_the_blackwell_units():
     for mnemonic, least in (("UTCHMMA", 8), ("LDTM", 3), ("UTMALDG", 8), ("UTMASTG", 4), ("LDGSTS", 8)):
         assert sass.count(mnemonic) >= least, f"{mnemonic}: {sass.count(mnemonic)} occurrences"
     assert "HMMA.16816" not in sass and "WGMMA" not in sass
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exactly one JSON line on stdout with the
+    contract's keys, whatever libraries write to file descriptor 1."""
+    import json
+    import subprocess
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1_384x512_b1",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    out = json.loads(lines[0])
+    assert out["impl"] == "reference" and out["unit"] == "pairs/s" and out["value"] > 0
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
+        assert key in out, key
+    assert out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["cores"] >= 1
+    assert out["e2e"]["h2d_bytes_per_step"] == 0 and out["e2e"]["d2h_bytes_per_step"] == 0

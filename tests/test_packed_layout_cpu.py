@@ -107,3 +107,30 @@ def test_blocks_cover_every_coordinate_with_a_live_tap():
     for x in (-40.0, -100.0, w + 32.0, w + 500.0):
         ref = O.closed_lookup([lv.reshape(1, 1, 1, -1) for lv in levels], np.array([[[x]]]), 4)
         assert np.abs(ref).max() == 0
+
+
+@pytest.mark.parametrize("w", [40, 312])
+def test_factored_line_is_the_combination_of_the_right_normal_lines(w):
+    """mono_mode "factored" (csrc/packed.cu, FV path): the packed line of the rank-3 mono volume row
+    V[w3] = k * sum_c nL[c] nR[c, w3] is, slot by slot, the combination of the packed lines of the three right-normal
+    rows with k * nL[c] as coefficients (one product + two FMAs per slot, as in the kernel)."""
+    f32 = np.float32
+    rng = np.random.RandomState(7 + w)
+    nr = rng.randn(3, w); nr = (nr / np.linalg.norm(nr, axis=0)).astype(f32)
+    nl = rng.randn(3); nl = (nl / np.linalg.norm(nl)).astype(f32)
+    k = f32(f32(1.73) * f32(1.0 / np.float64(f32(np.sqrt(3.0)))))
+    lines_c = [pack_row(O.closed_pyramid(nr[c], 4)) for c in range(3)]       # the 14 MB array of the kernel, one row
+    a = [f32(nl[c] * k) for c in range(3)]
+    comb = np.float64(a[0] * lines_c[0])                                     # FMUL
+    comb = f32(np.float64(a[1]) * np.float64(lines_c[1]) + comb)             # FFMA
+    comb = f32(np.float64(a[2]) * np.float64(lines_c[2]) + np.float64(comb)) # FFMA
+    vol_row = (1.73 * (nl.astype(np.float64) @ nr.astype(np.float64)) / np.float64(f32(np.sqrt(3.0))))
+    levels = O.closed_pyramid(vol_row, 4)                                    # float64 closed form of the volume row
+    xs = np.concatenate([rng.uniform(-45, w + 40, 300), np.arange(-41, w + 34, dtype=np.float64)]).astype(f32)
+    n = xs.shape[0]
+    ref = O.closed_lookup([np.broadcast_to(lv, (1, 1, n, lv.shape[0])) for lv in levels],
+                          xs.astype(np.float64).reshape(1, 1, n), 4)[0, :, 0, :]
+    for i, x in enumerate(xs):
+        q = (int(np.floor(x)) >> 3) - Q_MIN
+        got = lookup_from_line(comb[q], x) if 0 <= q < comb.shape[0] else np.zeros(36, f32)
+        assert np.abs(got - ref[:, i]).max() <= 2e-6, (w, float(x))

@@ -5,8 +5,11 @@ Run in the build container only (needs /root/reference):
 
     python tests/golden/make_golden.py
 
-Everything is seeded; re-running reproduces the committed files bit for bit on the same torch
-build (2.11.0+cu128, CPU, 8 threads).  Outputs:
+Everything is seeded.  On the same torch build (2.11.0+cu128, CPU, 8 threads) re-running reproduces
+path_small / tiles / reductions / grads bit for bit; model_slice (a whole-model forward: multi-threaded
+convolutions) and producers (QR `lstsq`) come back equal to fp32 rounding only (<= 2e-6 relative from run to
+run, checked) - each committed file is ONE self-consistent run of the reference, which is what the parity
+tests need (the lookups of model_slice were produced from the very volumes stored next to them).  Outputs:
 
 * path_small.npz   - corr / pyramid / lookup / truncation / bins / masked volume / gauss /
                      corruption on small seeded tensors (reference functions called directly).

@@ -8,20 +8,23 @@ Default workload = BASELINE.json configs[1]: KITTI-size 375x1242 pairs (padded t
 resolution 96x312), batch 8 per GPU, C=256, 4 levels, radius 4, 32 iterations.
 
     python bench.py                      # N=1, K=10, W=3
-    python bench.py --impl reference     # the reference's CPU op sequence (oracle port) on host cores
+    python bench.py --impl reference     # the reference's own CorrBlock1D (oracle/_ref) on the host cores
     torchrun --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM);
 `e2e` goes through the public CorrBlockB200 API from pinned HOST buffers with the H2D / D2H copies
 inside the timed region.  `roofline` is for the dominant kernel (the lookup), timed live with CUDA
-events inside the timed region; `cpu_baseline` is the oracle port timed on this box's host cores on
-a bounded sample.
+events inside the timed region; `cpu_baseline` is the reference's CorrBlock1D timed on this box's host
+cores on a bounded sample.  The default line also carries, measured in the same run:
+  `variants`  - the README wiring (`--mono aggregated`) and the strict drop-in call sequence (`--variant protocol`);
+  `tiled_c4`  - BASELINE config 4 (full-resolution Middlebury, reference tile geometry, tiles sharded over the N
+                ranks, collective-free stitch over NVLink peer memory), strong scaling, with the N-rank result
+                checked against the 1-rank result before the timed region.
 """
 from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -43,15 +46,24 @@ WORKLOADS = {
     "c5_sweep_c256_w768_b1": (1, 256, 96, 768),
 }
 DEFAULT_WORKLOAD = "c2_kitti_375x1242_b8"
+TILED_WORKLOAD = "c4_middlebury_1984x2872_tiled"
 ITERS, LEVELS, RADIUS = 32, 4, 4
 METRIC = "stereo pairs/sec @375x1242, 32 iters (cost-volume path: corr + pyramid + lookup)"
 METRIC_SIZES = {"c1_384x512_b1": "384x512", "c2_kitti_375x1242_b8": "375x1242", "c3_sceneflow_540x960_b8": "540x960",
                 "c4_middlebury_tile_1120x672_b1": "1120x672 (one Middlebury tile)", "c5_sweep_c256_w768_b1": "384x3072 (W/4 = 768)"}
+UNIT = "pairs/s"
 
 
 def metric_for(workload):
     return METRIC.replace("375x1242", METRIC_SIZES.get(workload, "375x1242"))
-UNIT = "pairs/s"
+
+
+def workload_config(workload, n_gpus):
+    """`config` of the JSON line: the workload only, identical in both arms (`--impl b200` / `--impl reference`)."""
+    b, c, h, w = WORKLOADS[workload]
+    return {"workload": workload, "pairs_per_gpu": b, "C": c, "H4": h, "W4": w, "iters": ITERS, "levels": LEVELS,
+            "radius": RADIUS, "l2": "inputs+volumes (>1 GB/step) exceed the 126 MB L2; no explicit flush",
+            "parallelism": f"batch-sharded x{n_gpus}, async all_gather of quarter-res disparity per step"}
 
 
 def tensor_peak_tf32():
@@ -107,7 +119,7 @@ def path_bytes(b, c, h, w):
 
 
 # ------------------------------------------------------------------------------------------
-# clocks sampler (nvidia-smi, 200 ms) - evidence that the timed region was not throttled
+# clocks sampler (nvidia-smi, 100 ms) - evidence that the timed region was not throttled
 # ------------------------------------------------------------------------------------------
 
 class ClockSampler:
@@ -159,13 +171,51 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
+# host placement: run on the CPUs next to this rank's GPU before any pinned buffer is allocated
+# ------------------------------------------------------------------------------------------
+
+def bind_to_gpu_numa(local):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (first-touch then places the pinned staging
+    buffers there).  Returns what was found; a single-node host (or a VM that hides the topology) is reported as is."""
+    info = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        hdl = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(hdl).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node_file = f"/sys/bus/pci/devices/{bus}/numa_node"
+        node = int(open(node_file).read().strip()) if os.path.exists(node_file) else -1
+        info["numa_node"] = node
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()] \
+            if os.path.isdir("/sys/devices/system/node") else []
+        info["host_numa_nodes"] = len(nodes)
+        if node >= 0 and len(nodes) > 1:
+            cpulist = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+            cpus = set()
+            for part in cpulist.split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                info["cpus"], info["bound"] = cpulist, True
+    except Exception as e:  # pragma: no cover - topology files differ between boxes
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info
+
+
+# ------------------------------------------------------------------------------------------
 # the path on the GPU, through the public API
 # ------------------------------------------------------------------------------------------
 
 class GpuPath:
     def __init__(self, sa, d, variant, mono="factored"):
         self.sa, self.d, self.variant, self.mono = sa, d, variant, mono
-        self.ev = None  # (start, end) events around the lookup loop of the current step
         self.launches = 0
 
     def build_stereo(self):
@@ -230,10 +280,112 @@ class GpuPath:
         return self.lookups(fs, fm, seq, timed_events)
 
 
-def run_gpu(args):
+def _ev():
+    return torch.cuda.Event(enable_timing=True)
+
+
+def measure_path(sa, d, variant, mono, steps, warmup, graph, after_step=None, drain=None, barrier=None):
+    """Time `steps` steps of the path on device-resident inputs `d` (CUDA events on the current stream).
+    Returns ms per step, ms per lookup launch, launches per step, and (fused + graph) the two builders timed alone."""
+    B = sa.CorrBlockB200
+    saved_mode = B.mono_mode
+    B.mono_mode = mono if mono != "aggregated" else "packed"
+    otf = variant == "fused" and mono == "otf"
+    path = GpuPath(sa, d, variant, mono)
+    out = None
+    try:
+        for _ in range(max(warmup, 3)):
+            out = path.step()
+            if after_step is not None:
+                after_step(out)
+        g_build = g_look = g_mono = None
+        if graph:
+            # The step is ~35 launches of 10-400 us: replay it from CUDA graphs (stereo volume + packing; mono
+            # packing; the 32 lookups) so that the events between the graphs time each kernel family alone.
+            torch.cuda.synchronize()
+            seq = path.coords_seq()
+            g_build, g_look = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            if otf:
+                with torch.cuda.graph(g_build):
+                    fs = path.build_stereo()
+                fm = path.build_mono()   # holds the normal maps only: no kernel, nothing to capture
+            elif variant == "fused":
+                g_mono = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_build):
+                    fs = path.build_stereo()
+                with torch.cuda.graph(g_mono, pool=g_build.pool()):
+                    fm = path.build_mono()
+            else:
+                with torch.cuda.graph(g_build):
+                    fs, fm = path.build()
+            with torch.cuda.graph(g_look, pool=g_build.pool()):
+                g_out = path.lookups(fs, fm, seq)
+            for _ in range(2):
+                g_build.replay()
+                if g_mono is not None:
+                    g_mono.replay()
+                g_look.replay()
+        if drain is not None:
+            drain()
+        if barrier is not None:
+            barrier()
+        else:
+            torch.cuda.synchronize()
+        path.launches = 0
+        lk_events = [(_ev(), _ev()) for _ in range(steps)]
+        e0, e1 = _ev(), _ev()
+        e0.record()
+        for k in range(steps):
+            if g_build is not None:
+                g_build.replay()
+                if g_mono is not None:
+                    g_mono.replay()
+                lk_events[k][0].record()
+                g_look.replay()
+                lk_events[k][1].record()
+                out = g_out
+            else:
+                out = path.step(lk_events[k])
+            if after_step is not None:
+                after_step(out)
+        if drain is not None:
+            drain()
+        e1.record()
+        if barrier is not None:
+            barrier()
+        else:
+            torch.cuda.synchronize()
+        ms_total = e0.elapsed_time(e1)
+        per_step = (33 if otf else 35 if mono == "aggregated" else 34) if variant == "fused" else 69
+        launches = path.launches if g_build is None else steps * per_step
+        lk_ms = sum(a.elapsed_time(bb) for a, bb in lk_events) / steps
+        breakdown = None
+        if g_build is not None and variant == "fused":
+            # per-kernel times of the two builders (one kernel per graph), measured AFTER the timed region so that no
+            # extra event sits between the graphs of a timed step: each graph replayed alone, the lookup graph in
+            # between so that the volumes of the previous replay are out of L2 as they are in a step
+            def alone(g):
+                ts = []
+                for _ in range(5):
+                    g_look.replay()
+                    a0, a1 = _ev(), _ev()
+                    a0.record(); g.replay(); a1.record(); torch.cuda.synchronize()
+                    ts.append(a0.elapsed_time(a1))
+                ts.sort()
+                return ts[len(ts) // 2]
+            breakdown = (alone(g_build), alone(g_mono) if g_mono is not None else None)
+        n_lk = ITERS if variant == "fused" else 2 * ITERS
+        return {"ms_step": ms_total / steps, "lk_launch_ms": lk_ms / n_lk, "n_lk_launch": n_lk, "launches": launches,
+                "breakdown": breakdown}
+    finally:
+        B.mono_mode = saved_mode
+
+
+def init_dist():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa(local)   # before the first pinned allocation / CUDA context
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -242,21 +394,31 @@ def run_gpu(args):
 
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
+    return rank, world, local, dev, dist, numa
+
+
+def run_gpu(args):
+    rank, world, local, dev, dist, numa = init_dist()
     import stereoanywhere_b200 as sa
 
     sa.CorrBlockB200.precision = args.precision
-    sa.CorrBlockB200.mono_mode = args.mono if args.mono != "aggregated" else "packed"
     otf = args.variant == "fused" and args.mono == "otf"
     factored = args.variant == "fused" and args.mono == "factored"
     b, c, h, w = WORKLOADS[args.workload]
     host, d = make_inputs(b, c, h, w, dev, seed=rank, pinned=True)
     torch.cuda.synchronize()
-    path = GpuPath(sa, d, args.variant, args.mono)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def maxr(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- device-resident throughput -------------------------------------------------------
     sampler = ClockSampler(local)
@@ -289,82 +451,34 @@ def run_gpu(args):
                 pending[i].wait()
                 pending[i] = None
 
-    for _ in range(max(args.warmup, 3)):
-        collective(path.step())
-    g_build = g_look = g_mono = None
-    if args.graph:
-        # The step is ~35 launches of 10-400 us: replay it from CUDA graphs (stereo volume + packing; mono packing;
-        # the 32 lookups) so that the events between the graphs time each kernel family alone.
-        torch.cuda.synchronize()
-        seq = path.coords_seq()
-        g_build, g_look = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        if otf:
-            with torch.cuda.graph(g_build):
-                fs = path.build_stereo()
-            fm = path.build_mono()   # holds the normal maps only: no kernel, nothing to capture
-        elif args.variant == "fused":
-            g_mono = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g_build):
-                fs = path.build_stereo()
-            with torch.cuda.graph(g_mono, pool=g_build.pool()):
-                fm = path.build_mono()
-        else:
-            with torch.cuda.graph(g_build):
-                fs, fm = path.build()
-        with torch.cuda.graph(g_look, pool=g_build.pool()):
-            g_out = path.lookups(fs, fm, seq)
-        for _ in range(2):
-            g_build.replay()
-            if g_mono is not None:
-                g_mono.replay()
-            g_look.replay()
-    drain()
-    barrier()
-    path.launches = 0
-    lk_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    bd_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(args.steps):
-        if g_build is not None:
-            g_build.replay()
-            if g_mono is not None:
-                g_mono.replay()
-            lk_events[k][0].record()
-            g_look.replay()
-            lk_events[k][1].record()
-            out = g_out
-        else:
-            out = path.step(lk_events[k])
-        collective(out)
-    drain()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    launches = path.launches if g_build is None else args.steps * (
-        (33 if otf else 35 if args.mono == "aggregated" else 34) if args.variant == "fused" else 69)
-    lk_ms = sum(a.elapsed_time(bb) for a, bb in lk_events) / args.steps
-    breakdown = None
-    if g_build is not None and args.variant == "fused":
-        # per-kernel times of the two builders (one kernel per graph), measured AFTER the timed region so that no
-        # extra event sits between the graphs of a timed step: each graph replayed alone, the lookup graph in
-        # between so that the volumes of the previous replay are out of L2 as they are in a step
-        def alone(g):
-            ts = []
-            for _ in range(5):
-                g_look.replay()
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record(); g.replay(); a1.record(); torch.cuda.synchronize()
-                ts.append(a0.elapsed_time(a1))
-            ts.sort()
-            return ts[len(ts) // 2]
-        breakdown = (alone(g_build), alone(g_mono) if g_mono is not None else None)
-    n_lk_launch = ITERS if args.variant == "fused" else 2 * ITERS
-    lk_launch_ms = lk_ms / n_lk_launch
+    m = measure_path(sa, d, args.variant, args.mono, args.steps, args.warmup, args.graph, after_step=collective,
+                     drain=drain, barrier=barrier)
+    ms_total, lk_launch_ms, launches, breakdown = m["ms_step"] * args.steps, m["lk_launch_ms"], m["launches"], m["breakdown"]
+    n_lk_launch = m["n_lk_launch"]
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the other two wirings of the same workload, same run (driver-measured) -------------------
+    variants = None
+    if args.extras and args.workload == DEFAULT_WORKLOAD and args.variant == "fused" and args.mono == "factored":
+        torch.cuda.empty_cache()
+        va = measure_path(sa, d, "fused", "aggregated", 5, 3, args.graph)
+        torch.cuda.empty_cache()
+        vp = measure_path(sa, d, "protocol", "packed", 5, 3, args.graph)
+        torch.cuda.empty_cache()
+        variants = {
+            "aggregated_mono_ms": round(maxr(va["ms_step"]), 4),
+            "protocol_ms": round(maxr(vp["ms_step"]), 4),
+            "steps": 5,
+            "aggregated_mono": "README wiring (--use_aggregate_mono_vol, stereoanywhere.py:162-165,210,257-259): mono volume "
+                               "materialised, mono block built from a dense volume (sa_pack_pyramid), dual packed lookup",
+            "protocol": "strict drop-in call sequence (INTEGRATION section 2, fused=False): corr() x2, 1.73*, truncation mask, "
+                        "product, two constructors, 64 single lookups",
+        }
 
     # ---- end to end through the public API from pinned host buffers ---------------------------
     # Every step uploads ITS OWN inputs from pinned host memory and reads its result back; the
     # upload of step k+1 runs on a copy stream while step k computes (two device buffer sets).
+    sa.CorrBlockB200.mono_mode = args.mono if args.mono != "aggregated" else "packed"
     keys = ["fl", "fr", "nl", "nr", "coords0", "delta", "tdisp", "tconf"]
     sets = [{k: torch.empty_like(d[k]) for k in keys} for _ in range(2)]
     res_s = torch.empty((b, LEVELS * (2 * RADIUS + 1), h, w), dtype=torch.float32).pin_memory()
@@ -393,15 +507,15 @@ def run_gpu(args):
             if k + 1 < n:
                 upload(i ^ 1)
             main_stream.wait_event(ready[i])
-            s, m, _ = paths[i].step()
+            s, mm, _ = paths[i].step()
             freed[i].record(main_stream)
             res_s.copy_(s, non_blocking=True)
-            res_m.copy_(m, non_blocking=True)
+            res_m.copy_(mm, non_blocking=True)
 
     e2e_run(3)
     barrier()
     t0 = time.perf_counter()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0, f1 = _ev(), _ev()
     f0.record()
     e2e_run(args.steps)
     f1.record()
@@ -409,18 +523,34 @@ def run_gpu(args):
     e2e_ms = f0.elapsed_time(f1)
     e2e_wall = (time.perf_counter() - t0) * 1e3
 
-    def maxr(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    # the ceiling of that number: the same uploads with NO compute, all ranks at once (what the host side - PCIe
+    # links, root complexes, host DRAM - delivers to N GPUs simultaneously)
+    def copy_only(n):
+        with torch.cuda.stream(copy_stream):
+            for _ in range(n):
+                for k in keys:
+                    sets[0][k].copy_(host[k], non_blocking=True)
 
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total, e2e_ms, lk_launch_ms = maxr(ms_total), maxr(max(e2e_ms, 0.0)), maxr(lk_launch_ms)
+    copy_only(1)
+    barrier()
+    c0, c1 = _ev(), _ev()
+    with torch.cuda.stream(copy_stream):
+        c0.record(copy_stream)
+    copy_only(3)
+    with torch.cuda.stream(copy_stream):
+        c1.record(copy_stream)
+    barrier()
+    copy_ms = c0.elapsed_time(c1) / 3
+
+    ms_total, e2e_ms, lk_launch_ms, copy_ms = maxr(ms_total), maxr(max(e2e_ms, 0.0)), maxr(lk_launch_ms), maxr(copy_ms)
     ms_step = ms_total / args.steps
     value = world * b / (ms_step / 1e3)
     e2e_value = world * b / (e2e_ms / args.steps / 1e3)
+
+    tiled = None
+    if args.extras and args.tiled:
+        torch.cuda.empty_cache()
+        tiled = tiled_measure(sa, dev, rank, world, dist, args, steps=max(5, min(args.steps, 20)), warmup=3)
 
     result = None
     if rank == 0:
@@ -433,16 +563,16 @@ def run_gpu(args):
         real_px = (416 if otf else 432 if factored else 544)
         alg = alg_px * p
         achieved = alg / (lk_launch_ms * 1e-3) / 1e9
+        s8d = 612 if args.variant == "fused" else 308
         roof = {"bound": "hbm", "kernel": "lookup_packed_kernel" + ("<NV=2>" if args.variant == "fused" else "<NV=1>"),
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": TRAFFIC_BYTES.get((args.workload, args.variant, "packed" if args.mono == "aggregated" else args.mono)), "peak_source": peak_src,
-                "algorithmic_bytes_per_pixel": alg_px,
+                "traffic": TRAFFIC_BYTES.get((args.workload, args.variant, "packed" if args.mono == "aggregated" else args.mono)),
+                "peak_source": peak_src, "algorithmic_bytes_per_pixel": alg_px,
                 "algorithmic_bytes_per_launch": alg, "launch_us": round(lk_launch_ms * 1e3, 2),
                 # SURVEY 8d counts 612 B/px for the dual lookup (both volumes' windows read from memory); the factored
                 # and on-the-fly forms do not read the mono windows, `achieved` above uses their own smaller figure
-                "survey_8d_definition": {"bytes_per_pixel": 612 if args.variant == "fused" else 308,
-                                         "gbs": round((612 if args.variant == "fused" else 308) * p / (lk_launch_ms * 1e-3) / 1e9, 1),
-                                         "frac": round((612 if args.variant == "fused" else 308) * p / (lk_launch_ms * 1e-3) / 1e9 / peak, 4)},
+                "survey_8d_definition": {"bytes_per_pixel": s8d, "gbs": round(s8d * p / (lk_launch_ms * 1e-3) / 1e9, 1),
+                                         "frac": round(s8d * p / (lk_launch_ms * 1e-3) / 1e9 / peak, 4)},
                 "path_algorithmic_gbs": round(path_bytes(b, c, h, w) / (ms_step * 1e-3) / 1e9, 1)}
         kernels = None
         if breakdown is not None:
@@ -472,28 +602,35 @@ def run_gpu(args):
                                    "hbm_gbs_real_bytes": round(real_px * p / (lk_launch_ms * 1e-3) / 1e9, 1),
                                    "hbm_frac_real_bytes": round(real_px * p / (lk_launch_ms * 1e-3) / 1e9 / peak, 4)},
             }
+            roof["kernels"] = kernels   # also inside `roofline`: the driver's parser keeps this object whole
         cpu = None if args.no_cpu_baseline else cpu_baseline(args.workload, sample_pairs=args.cpu_pairs, reps=3)
+        copy_gbs = h2d / (copy_ms * 1e-3) / 1e9
         result = {
             "metric": metric_for(args.workload), "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": f"{args.precision} corr (fp32 accumulate), f32 pyramid/lookup",
             "data": "synthetic (seeded N(0,1) features, unit normals, U(0,W/4) disparities)",
-            "config": {"workload": args.workload, "pairs_per_gpu": b, "C": c, "H4": h, "W4": w, "iters": ITERS,
-                       "levels": LEVELS, "radius": RADIUS, "variant": args.variant, "cuda_graph": bool(args.graph),
-                       "mono": ("on the fly: lookups computed from the normal maps inside the lookup kernel, bit-identical to "
-                                "the packed pyramid (no mono volume / pyramid in memory)") if otf else
-                               ("factored: packed pyramid of the right normal map's rows (rank-3 volume, linear pyramid); "
-                                "the lookup combines three lines with the pixel's left normal") if factored else
-                               ("aggregated (README configuration): dense mono volume materialised, block built from a "
-                                "dense volume") if args.mono == "aggregated" else "packed pyramid",
-                       "l2": "inputs+volumes (>1 GB/step) exceed the 126 MB L2; no explicit flush",
-                       "parallelism": f"batch-sharded x{world}, async all_gather of quarter-res disparity per step"},
+            "config": workload_config(args.workload, world),
+            "impl_config": {"variant": args.variant, "cuda_graph": bool(args.graph),
+                            "mono": ("on the fly: lookups computed from the normal maps inside the lookup kernel, bit-identical to "
+                                     "the packed pyramid (no mono volume / pyramid in memory)") if otf else
+                                    ("factored: packed pyramid of the right normal map's rows (rank-3 volume, linear pyramid); "
+                                     "the lookup combines three lines with the pixel's left normal") if factored else
+                                    ("aggregated (README configuration): dense mono volume materialised, block built from a "
+                                     "dense volume") if args.mono == "aggregated" else "packed pyramid"},
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(e2e_ms / args.steps, 4), "wall_ms_per_step": round(e2e_wall / args.steps, 4)},
+                    "ms_per_step": round(e2e_ms / args.steps, 4), "wall_ms_per_step": round(e2e_wall / args.steps, 4),
+                    # the bound, measured: the same uploads with no compute, all ranks at once (max over ranks)
+                    "h2d_only_ms_per_step": round(copy_ms, 4), "h2d_gbs_per_rank": round(copy_gbs, 1),
+                    "h2d_gbs_all_ranks": round(copy_gbs * world, 1),
+                    "copy_bound_value": round(world * b / (copy_ms / 1e3), 2),
+                    "host_binding": numa},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,
             "kernels": kernels,
+            "variants": variants,
+            "tiled_c4": tiled,
             "cpu_baseline": cpu,
         }
         emit(result)
@@ -507,175 +644,173 @@ def run_gpu(args):
 # config 4: full-resolution Middlebury, tiles sharded over the ranks (strong scaling)
 # ------------------------------------------------------------------------------------------
 
-def run_tiled(args):
-    """`--workload c4_middlebury_1984x2872_tiled`: K full-resolution pairs per step, reference tile
-    geometry (`--tile-preset`, distinct tiles weighted by multiplicity), every tile runs the whole hot
-    path at its quarter resolution, per-rank cosine-blend accumulation, ONE asynchronous reduce(sum) of
-    [images,H,W] per step to rank 0.  Path-only: the per-tile disparity is the final lookup coordinate field upsampled
-    x4 (the encoders / GRU that would produce it are out of scope)."""
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist_
-
-        dist = dist_
-        dist.init_process_group("nccl", device_id=dev)
-    import stereoanywhere_b200 as sa
+def tiled_measure(sa, dev, rank, world, dist, args, steps, warmup):
+    """BASELINE config 4: `args.images` full-resolution pairs per step, reference tile geometry (`--tile-preset`,
+    distinct tiles weighted by multiplicity, mapreduce_v2/tile_wrapper.py:101-120), every tile runs the whole hot path
+    at its quarter resolution (one tile at a time, as the reference does), and `tiling.SlotStitcher` stitches without a
+    collective: the rank that ran a tile stores the weighted tile straight into rank 0's memory (NVLink peer stores,
+    `sa_stitch_tile`), rank 0 sums the slots in enumeration order and normalises (`sa_stitch_finish`).  Path-only:
+    a tile's disparity is its final lookup coordinate field (the encoders / GRU that would produce it are out of
+    scope).  Before the timed region rank 0 checks the N-rank image against the image it computes alone."""
     from stereoanywhere_b200 import tiling
 
-    sa.CorrBlockB200.precision = args.precision
-    sa.CorrBlockB200.mono_mode = args.mono if args.mono != "aggregated" else "packed"
     B = sa.CorrBlockB200
+    saved_mode, B.mono_mode = B.mono_mode, (args.mono if args.mono in ("factored", "packed", "otf") else "packed")
     H, W = 1984, 2880                      # 1984x2872 replicate-padded to /32 (test_mapreduce_v2.py:217-227)
     th, tw, ov = tiling.PRESETS[args.tile_preset]
     work = tiling.tile_multiplicity(H, W, th, tw, ov)
-    units = [(img, t, m) for img in range(args.images) for (t, m) in work]
-    mine = tiling.shard(units, rank, world)
-    shapes = sorted({((t[1] - t[0] + sum(tiling.pad_to_32(t[1] - t[0], t[3] - t[2])[2:])) // 4,
-                      (t[3] - t[2] + sum(tiling.pad_to_32(t[1] - t[0], t[3] - t[2])[:2])) // 4) for _, t, _ in units})
-    inputs = {hw: make_inputs(1, 256, hw[0], hw[1], dev, seed=rank)[1] for hw in shapes}
-    weights = {}
-    torch.cuda.synchronize()
+    images = args.images
+
+    def geometry(tile):
+        y0, y1, x0, x1 = tile
+        pad = tiling.pad_to_32(y1 - y0, x1 - x0)
+        return pad, ((y1 - y0 + pad[2] + pad[3]) // 4, (x1 - x0 + pad[0] + pad[1]) // 4)
 
     def tile_path(d):
         fs = B.from_features(d["fl"], d["fr"], radius=RADIUS, num_levels=LEVELS, truncate=(d["tdisp"], d["tconf"], 0.9))
         fm = B.from_normals(d["nl"], d["nr"], radius=RADIUS, num_levels=LEVELS)
         coords = d["coords0"]
         for _ in range(ITERS):
-            s, m = B.lookup_pair(fs, fm, coords)
+            B.lookup_pair(fs, fm, coords)
             coords = coords + d["delta"]
-        q = (d["coords0"] - coords)[:, :1]  # quarter-res disparity, positive
-        return torch.nn.functional.interpolate(q, scale_factor=4, mode="nearest") * 4.0
+        return (d["coords0"] - coords)[:, :1].contiguous()   # quarter-resolution disparity, positive
 
-    # one tile = ~100 launches of 3-60 us: replay it from a CUDA graph per tile shape (the stitch stays eager)
-    graphs = {}
-    if args.graph:
-        for hw, d in inputs.items():
-            for _ in range(2):
-                tile_path(d)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                out = tile_path(d)
-            graphs[hw] = (g, out)
+    pool = [None]
+    runners = {}
 
-    def run_tile(hw):
-        if hw in graphs:
-            graphs[hw][0].replay()
-            return graphs[hw][1]
-        return tile_path(inputs[hw])
+    def runner(img, hw):
+        """Inputs (seeded by image and tile shape: the same on every rank) + the CUDA graph of one tile run."""
+        key = (img, hw)
+        if key not in runners:
+            d = make_inputs(1, 256, hw[0], hw[1], dev, seed=1000 + 16 * img + (hw[0] * 7 + hw[1]) % 16)[1]
+            if not args.graph:
+                runners[key] = (None, d, None)
+            else:
+                for _ in range(2):
+                    tile_path(d)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool[0]):
+                    q = tile_path(d)
+                if pool[0] is None:
+                    pool[0] = g.pool()
+                runners[key] = (g, d, q)
+        return runners[key]
 
-    # accumulator [images, H, W] of disp*w, double-buffered: the reduce(sum) of step k runs on NCCL's stream
-    # while step k+1 computes; it is waited for when its buffer comes round again (step k+2) and before the
-    # closing event of the timed region.  The weight plane sum(w) depends on the geometry only: rank 0 forms
-    # it once (tiling.weight_sum) instead of reducing it every step.
-    stitcher = None
-    istitch = None
-    if dist is not None and args.stitch == "image" and tiling.plan_images(args.images, world) is not None:
-        # tiles sharded by image: only the ranks that share an image reduce its plane, leaders send finished planes
-        istitch = tiling.ImageStitcher(args.images, H, W, work, dev)
-        mine = istitch.units(work)
-    if dist is not None and args.stitch == "peer":
-        # reduce + normalise + gather over NVLink peer memory in one kernel per rank (tiling.PeerStitcher) instead of
-        # an SM-resident NCCL reduce next to the persistent GEMM kernels; falls back to NCCL if symmetric memory
-        # cannot be set up on this box
-        try:
-            stitcher = tiling.PeerStitcher(args.images, H, W, tiling.weight_sum(H, W, work, device=dev), dev)
-        except Exception as e:  # pragma: no cover
-            if rank == 0:
-                print(f"[bench] peer stitch unavailable ({type(e).__name__}: {e}); using NCCL reduce", file=sys.stderr)
-            stitcher = None
-    acc_bufs = [torch.empty(args.images, H, W, device=dev) for _ in range(2)] if stitcher is None and istitch is None else None
-    den = torch.clamp(tiling.weight_sum(H, W, work, device=dev), min=1e-4) if rank == 0 and istitch is None else None
-    pending = [None, None]
-    step_no = [0]
-
-    def finish(i):
-        if pending[i] is not None:
-            if pending[i] != "local":
-                pending[i].wait()
-            pending[i] = None
-            if rank == 0:
-                return acc_bufs[i] / den
-        return None
-
-    def step():
-        i = step_no[0] & 1
-        step_no[0] += 1
-        if istitch is not None:
-            accs = istitch.buffer(i)
-        elif stitcher is not None:
-            accs = stitcher.buffer(i)
+    def run_unit(st, u):
+        img, tile, _mult = st.units[u]
+        pad, hw = geometry(tile)
+        g, d, q = runner(img, hw)
+        if g is None:
+            q = tile_path(d)
         else:
-            finish(i)
-            accs = acc_bufs[i]
-        accs.zero_()
-        for img, (y0, y1, x0, x1), mult in mine:
-            pad = tiling.pad_to_32(y1 - y0, x1 - x0)
-            hw = ((y1 - y0 + pad[2] + pad[3]) // 4, (x1 - x0 + pad[0] + pad[1]) // 4)
-            full = run_tile(hw)
-            full = full[..., pad[2]: full.shape[-2] - pad[3], pad[0]: full.shape[-1] - pad[1]]
-            key = (y1 - y0, x1 - x0, mult)
-            if key not in weights:
-                weights[key] = tiling.blend_weight(key[0], key[1], device=dev) * float(mult)
-            accs[img if istitch is None else istitch.slot[img], y0:y1, x0:x1].addcmul_(full[0, 0], weights[key])
-        if istitch is not None:
-            istitch.launch(i)
-        elif stitcher is not None:
-            stitcher.reduce_to(i, 0)
-        else:
-            pending[i] = dist.reduce(accs, dst=0, op=dist.ReduceOp.SUM, async_op=True) if dist is not None else "local"
+            g.replay()
+        st.add(u, q, up=4, scale=4.0, pad_top=pad[2], pad_left=pad[0])
+        return q
 
-    def drain():
-        if istitch is not None:
-            return [istitch.drain()]
-        if stitcher is not None:
-            stitcher.drain()
-            return [stitcher.result()]
-        outs = [finish(i) for i in range(2)]
-        return outs
+    def step(st, units):
+        st.begin()
+        for u in units:
+            run_unit(st, u)
+        st.end()
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    drain()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    drain()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    try:
+        st = tiling.SlotStitcher(images, H, W, work, dev)
+        mine = st.my_units()
+        # ---- correctness before speed: N ranks against one rank, and against the host stitch -----------------
+        step(st, mine)
+        got = st.drain()
+        check = None
+        if rank == 0:
+            got = got.clone()
+            torch.cuda.synchronize()
+            if world > 1:
+                solo = tiling.SlotStitcher(images, H, W, work, dev, local=True)
+                step(solo, solo.my_units())
+                alone = solo.drain().clone()
+            else:
+                solo, alone = st, got
+            # host stitch (round 1's eager accumulate, the arithmetic of tiling.tiled_inference) of the same tiles
+            acc = torch.zeros(images, H, W, device=dev)
+            for u in range(len(solo.units)):
+                img, (y0, y1, x0, x1), mult = solo.units[u]
+                pad, hw = geometry((y0, y1, x0, x1))
+                g, d, q = runner(img, hw)
+                if g is None:
+                    q = tile_path(d)
+                else:
+                    g.replay()
+                full = torch.nn.functional.interpolate(q, scale_factor=4, mode="nearest") * 4.0
+                full = full[..., pad[2]: full.shape[-2] - pad[3], pad[0]: full.shape[-1] - pad[1]]
+                acc[img, y0:y1, x0:x1].addcmul_(full[0, 0], tiling.blend_weight(y1 - y0, x1 - x0, device=dev) * float(mult))
+            host = acc / torch.clamp(tiling.weight_sum(H, W, work, device=dev), min=1e-4)
+            check = {"n_rank_vs_1_rank_max_abs": float((got - alone).abs().max()),
+                     "vs_host_stitch_max_abs": float((alone - host).abs().max()),
+                     "mean_abs_disparity": float(host.abs().mean())}
+            del acc, host, alone
+            if world > 1:
+                del solo
+            assert check["n_rank_vs_1_rank_max_abs"] <= 1e-4 and check["vs_host_stitch_max_abs"] <= 1e-3 * max(
+                1.0, check["mean_abs_disparity"]), f"tile stitch is wrong: {check}"
+        barrier()
+        for _ in range(max(warmup, 3)):
+            step(st, mine)
+        st.drain()
+        barrier()
+        e0, e1 = _ev(), _ev()
+        e0.record()
+        for _ in range(steps):
+            step(st, mine)
+        st.drain()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        ms_step = ms / steps
+        out = {"metric": "stereo pairs/sec @1984x2872 tiled (cost-volume path per tile, 32 iters)",
+               "value": round(images / (ms_step / 1e3), 3), "unit": UNIT, "n_gpus": world, "steps": steps,
+               "ms_per_step": round(ms_step, 4), "scaling": "strong", "images_per_step": images,
+               "tile_preset": args.tile_preset, "distinct_tiles_per_image": len(work), "tiles_this_rank": len(mine),
+               "tiles_per_step": len(st.units), "cuda_graph": bool(args.graph),
+               "mono": B.mono_mode,
+               "stitch": ("slots over NVLink peer memory: one sa_stitch_tile per tile stores the weighted tile into rank 0, "
+                          "sa_stitch_finish sums in enumeration order and normalises; no collective") if world > 1 else
+                         "slots (local): sa_stitch_tile per tile + sa_stitch_finish",
+               "stitch_check": check}
+        del st
+        runners.clear()
+        torch.cuda.empty_cache()
+        return out
+    finally:
+        B.mono_mode = saved_mode
+
+
+def run_tiled(args):
+    rank, world, local, dev, dist, _numa = init_dist()
+    import stereoanywhere_b200 as sa
+
+    sa.CorrBlockB200.precision = args.precision
+    sampler = ClockSampler(local)
     if rank == 0:
-        ms_step = ms / args.steps
-        emit({
-            "metric": "stereo pairs/sec @1984x2872 tiled (cost-volume path per tile, 32 iters)", "value": round(args.images / (ms_step / 1e3), 3),
-            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 3),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": f"{args.precision} corr, f32 pyramid/lookup",
-            "data": "synthetic", "config": {"workload": args.workload, "images_per_step": args.images, "tile_preset": args.tile_preset,
-                                           "distinct_tiles_per_image": len(work), "tiles_this_rank": len(mine),
-                                           "cuda_graph": bool(args.graph),
-                                           "parallelism": (f"tiles sharded x{world} image by image ({len(istitch.ranks_of[0])} rank(s) per image): "
-                                                           f"async sub-group reduce of one [H,W] plane, leaders normalise and send "
-                                                           f"the finished planes to rank 0") if istitch is not None else
-                                                          (f"tiles sharded x{world}, stitch = reduce + normalise + gather over NVLink peer memory, one "
-                                                           f"kernel per rank (sa_peer_reduce), side stream") if stitcher is not None else
-                                                          f"tiles sharded x{world}, one async NCCL reduce(sum) of [images,H,W] per step"},
-        })
+        sampler.start()
+    t = tiled_measure(sa, dev, rank, world, dist, args, steps=args.steps, warmup=args.warmup)
+    if rank == 0:
+        clocks = sampler.stop()
+        emit({"metric": t["metric"], "value": t["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+              "warmup": max(args.warmup, 3), "ms_per_step": t["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+              "vs_baseline": None, "dtype": f"{args.precision} corr, f32 pyramid/lookup", "data": "synthetic",
+              "config": {"workload": TILED_WORKLOAD, **{k: t[k] for k in ("images_per_step", "tile_preset",
+                         "distinct_tiles_per_image", "tiles_this_rank", "tiles_per_step", "cuda_graph", "mono", "stitch")},
+                         "parallelism": f"tiles sharded x{world}, collective-free stitch"},
+              "stitch_check": t["stitch_check"], "clocks": clocks})
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -694,38 +829,50 @@ TRAFFIC_BYTES = {
 
 
 # ------------------------------------------------------------------------------------------
-# CPU: the reference's op sequence (oracle port)
+# CPU: the reference's own classes (oracle/_ref), else the oracle port
 # ------------------------------------------------------------------------------------------
 
-def cpu_once(workload, pairs):
+def cpu_runner():
+    """(callable, kind, description): the reference's own `CorrBlock1D` when its files are present (`/root/reference`
+    in the build container, the prebuilt `oracle/_ref` on the GPU box), else the oracle's restatement."""
+    from oracle import ref_path
+
+    if ref_path.available():
+        return ref_path.run_path_reference, "reference", ("oracle/ref_path.run_path_reference: the reference's own "
+                                                          "CorrBlock1D / truncate_corr_volume_v2 (unmodified files)")
     from oracle import corr_oracle as O
 
+    return O.run_path_cpu, "port", "oracle/corr_oracle.run_path_cpu (restatement of the reference ATen op sequence)"
+
+
+def cpu_once(workload, pairs, fn):
     b, c, h, w = WORKLOADS[workload]
     pairs = min(pairs, b)
     host, _ = make_inputs(pairs, c, h, w, None, seed=0)
     coords = [host["coords0"] + k * host["delta"] for k in range(ITERS)]
     t0 = time.perf_counter()
     with torch.no_grad():
-        O.run_path_cpu(host["fl"], host["fr"], host["nl"], host["nr"], coords,
-                       trunc=(host["tdisp"], host["tconf"], 0.9), radius=RADIUS, num_levels=LEVELS)
+        fn(host["fl"], host["fr"], host["nl"], host["nr"], coords, trunc=(host["tdisp"], host["tconf"], 0.9),
+           radius=RADIUS, num_levels=LEVELS)
     return time.perf_counter() - t0, pairs
 
 
 def cpu_baseline(workload, sample_pairs=8, reps=3, min_seconds=10.0):
     """Bounded CPU sample: whole batches of the workload until >= min_seconds of work (>= reps batches)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    cpu_once(workload, 1)  # warm-up (thread pool, allocator)
+    fn, kind, what = cpu_runner()
+    cpu_once(workload, 1, fn)  # warm-up (thread pool, allocator)
     total_t, total_pairs, n = 0.0, 0, 0
     while n < reps or total_t < min_seconds:
-        dt, pairs = cpu_once(workload, sample_pairs)
+        dt, pairs = cpu_once(workload, sample_pairs, fn)
         total_t += dt
         total_pairs += pairs
         n += 1
         if n >= 64:
             break
-    return {"value": round(total_pairs / total_t, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": round(total_pairs / total_t, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
             "sample": f"{n} x {pairs} of {WORKLOADS[workload][0]} pairs of {workload}, all {ITERS} iterations, "
-                      f"oracle/corr_oracle.run_path_cpu (reference ATen op sequence), {total_t:.1f} s of CPU work",
+                      f"{what}, {total_t:.1f} s of CPU work",
             "host_cpus": os.cpu_count()}
 
 
@@ -734,23 +881,23 @@ def run_reference(args):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
+    fn, kind, what = cpu_runner()
     b = WORKLOADS[args.workload][0]
     pairs = min(args.cpu_pairs, b)
-    for _ in range(min(args.warmup, 1)):
-        cpu_once(args.workload, pairs)
+    for _ in range(args.warmup):
+        cpu_once(args.workload, pairs, fn)
     t = 0.0
     for _ in range(args.steps):
-        dt, _ = cpu_once(args.workload, pairs)
+        dt, _ = cpu_once(args.workload, pairs, fn)
         t += dt
     value = pairs * args.steps / t
-    sample = (f"each step = {pairs} of {b} pairs of {args.workload}, all {ITERS} iterations, oracle port of the "
-              f"reference op sequence (einsum, avg_pool2d, grid_sample) on CPU")
+    sample = (f"each step = {pairs} of {b} pairs of {args.workload}, all {ITERS} iterations, {what} on the host cores")
     emit({
         "impl": "reference", "metric": metric_for(args.workload), "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": round(t / args.steps * 1e3, 2),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t / args.steps * 1e3, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "pairs_per_step": pairs, "iters": ITERS, "levels": LEVELS, "radius": RADIUS},
-        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "config": workload_config(args.workload, args.gpus),
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
@@ -782,14 +929,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + ["c4_middlebury_1984x2872_tiled"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + [TILED_WORKLOAD])
     ap.add_argument("--tile-preset", default="middlebury", help="reference tile preset for the tiled workload")
     ap.add_argument("--images", type=int, default=4, help="full-resolution pairs per step of the tiled workload")
-    ap.add_argument("--stitch", default="nccl", choices=["image", "peer", "nccl"],
-                    help="tiled workload, N > 1: 'nccl' = one async global reduce of [images,H,W] (default, measured fastest); "
-                         "'image' = tiles sharded image by image, sub-group reduce of single planes + send of the finished "
-                         "planes (tiling.ImageStitcher; falls back to 'nccl' when images and ranks do not divide); 'peer' = "
-                         "reduce + normalise + gather over NVLink peer memory (tiling.PeerStitcher / sa_peer_reduce)")
     ap.add_argument("--variant", default="fused", choices=["fused", "protocol"],
                     help="fused: truncate= / mono_corr / lookup_pair entry points; protocol: the reference's exact call sequence")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"], help="stereo correlation kernel")
@@ -800,8 +942,10 @@ def main():
     ap.add_argument("--graph", type=int, default=1, help="replay the step from a CUDA graph in the device-resident run")
     ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", type=int, default=1, help="0: skip the `variants` and `tiled_c4` objects (profiling runs)")
+    ap.add_argument("--tiled", type=int, default=1, help="0: skip the `tiled_c4` object of the default line")
     args = ap.parse_args()
-    if args.workload == "c4_middlebury_1984x2872_tiled":
+    if args.workload == TILED_WORKLOAD:
         if args.impl == "reference":
             args.workload = "c4_middlebury_tile_1120x672_b1"  # one reference tile as the bounded CPU sample
             run_reference(args)

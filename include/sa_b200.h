@@ -207,13 +207,25 @@ int sa_pyramid_backward(float* d0, const float* const* h_dlevels, const int* h_w
                         int num_levels, int64_t rows, const float* trunc_disp, const float* trunc_conf, double trunc_gain,
                         int w2_size, void* stream);
 
-/* ---------------------------------------------------------------- config 4: stitch over peer memory
- * dst[i] = (sum_k h_srcs[k][i]) / den[i]  (den == NULL: plain sum), i < n, n % 4 == 0.
- * h_srcs is a HOST array of n_src (<= 16) device pointers that may live on other GPUs of the node (NVLink peer
- * access enabled, e.g. torch symmetric memory): every rank reduces its slice of the per-rank accumulators
- * `sum disp * w` of the tile-sharded inference, normalises it by the weight plane and stores it into the
- * gathering rank's output (mapreduce_v2/tile_wrapper.py:185,340-362) - reduce + normalise + gather in one pass. */
-int sa_peer_reduce(const float* const* h_srcs, int n_src, const float* den, float* dst, int64_t n, void* stream);
+/* ---------------------------------------------------------------- config 4: tile stitch (no collective)
+ * Replaces the accumulate / normalise of `TileWrapper` (mapreduce_v2/tile_wrapper.py:172-185, :206, :226-247,
+ * :340-362) for tile-sharded inference on one node.
+ *   sa_stitch_tile    slot[y, x] = src[(y + pad_top) / up, (x + pad_left) / up] * scale * weight[y, x] * mult for the
+ *                     un-padded th x tw tile (tw % 4 == 0).  `src` is the tile's result, src_h x src_w floats: the
+ *                     padded full-resolution model output (up = 1, scale = -1: the reference negates it) or a
+ *                     quarter-resolution disparity (up = 4, scale = 4).  `weight` is the cosine blend window
+ *                     (tile_wrapper.py:36-49), `mult` the number of times the reference emits this tile.  `slot`
+ *                     (th * tw floats, 16-byte aligned) may live on ANOTHER GPU of the node (NVLink peer pointer,
+ *                     e.g. a torch symmetric-memory buffer): the stores are the gather.
+ *   sa_stitch_finish  out[img, y, x] = (sum of the slots of the tiles covering (img, y, x), in table order) /
+ *                     den[y, x].  tile_table: n_tiles x 6 DEVICE ints {image, y0, y1, x0, x1, slot offset in floats
+ *                     / 4}, x0 and x1 multiples of 4, listed in the reference's enumeration order; den: [H, W],
+ *                     already clamped (tile_wrapper.py:185); out: [images, H, W].  Table order fixes the summation
+ *                     order: the result is independent of which GPU produced which tile. */
+int sa_stitch_tile(const float* src, int src_h, int src_w, int up, float scale, int pad_top, int pad_left, int th, int tw,
+                   const float* weight, float mult, float* slot, void* stream);
+int sa_stitch_finish(const float* slots, const int* tile_table, int n_tiles, const float* den, float* out, int images,
+                     int H, int W, void* stream);
 
 /* ---------------------------------------------------------------- A5: truncation mask (standalone)
  * mask[b,h,w2,w3] = (1-c) + c * (sigmoid((w2 - d) - w3) * (1-g) + g); writes `out` = mask * vol

@@ -2,8 +2,11 @@
 
 TEST INFRASTRUCTURE ONLY.  This module exists so that `tests/golden/make_golden.py`
 can run the real reference code in the build container and freeze its outputs as
-fixtures.  `/root/reference` does not exist on the GPU box, so nothing under
-`tests/ -m gpu`, `__graft_entry__.smoke()` or `bench.py` imports this file.
+fixtures, and so that the GPU tests / `bench.py --impl reference` can run the reference's
+own classes on the GPU box.  `/root/reference` does not exist there: the unmodified files
+of the path travel in the git-ignored `oracle/_ref/` (recipe: `oracle/make_ref.py`, run by
+`__graft_entry__.build()`), and `REFERENCE_ROOT` falls back to it.  The product package
+never imports this file.
 
 The reference needs four third-party packages that are absent from this image and
 that the hot path never executes:
@@ -27,7 +30,19 @@ import types
 import torch
 import torch.nn.functional as F
 
-REFERENCE_ROOT = os.environ.get("SA_REFERENCE_ROOT", "/root/reference")
+_PREBUILT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _root() -> str:
+    env = os.environ.get("SA_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/models/stereoanywhere"):
+        return "/root/reference"
+    return _PREBUILT
+
+
+REFERENCE_ROOT = _root()
 
 
 def reference_available() -> bool:

@@ -59,8 +59,10 @@ def _declare(lib):
     lib.sa_lookup_packed_normals.argtypes = [vp, vp, vp, f, f, i, vp, i64, vp, vp, i, i, i, vp]
     lib.sa_lookup_packed_factored.restype = i
     lib.sa_lookup_packed_factored.argtypes = [vp, vp, vp, f, f, i, vp, i64, vp, vp, i, i, i, vp]
-    lib.sa_peer_reduce.restype = i
-    lib.sa_peer_reduce.argtypes = [vp, i, vp, vp, i64, vp]
+    lib.sa_stitch_tile.restype = i
+    lib.sa_stitch_tile.argtypes = [vp, i, i, i, f, i, i, i, i, vp, f, vp, vp]
+    lib.sa_stitch_finish.restype = i
+    lib.sa_stitch_finish.argtypes = [vp, vp, i, vp, vp, i, i, i, vp]
     lib.sa_lookup_packed_conv.restype = i
     lib.sa_lookup_packed_conv.argtypes = [vp, vp, i, vp, i64, vp, vp, vp, vp, i, i, i, vp]
     lib.sa_lookup_factored_conv.restype = i
@@ -75,7 +77,7 @@ def _declare(lib):
 
 EXPORTS = [
     "sa_abi_version", "sa_last_error", "sa_corr_fp32", "sa_corr_tf32", "sa_pyramid", "sa_lookup", "sa_lookup2",
-    "sa_truncate", "sa_masked_volume", "sa_corrupt", "sa_packed_row_floats", "sa_pack_pyramid", "sa_pack_pyramid_normals", "sa_lookup_packed", "sa_lookup_packed_conv", "sa_lookup_factored_conv", "sa_corr_pack_tf32", "sa_peer_reduce", "sa_lookup_packed_normals", "sa_lookup_packed_factored", "sa_lookup_backward", "sa_pyramid_backward", "sa_volume_softargmax", "sa_volume_entropy_conf",
+    "sa_truncate", "sa_masked_volume", "sa_corrupt", "sa_packed_row_floats", "sa_pack_pyramid", "sa_pack_pyramid_normals", "sa_lookup_packed", "sa_lookup_packed_conv", "sa_lookup_factored_conv", "sa_corr_pack_tf32", "sa_stitch_tile", "sa_stitch_finish", "sa_lookup_packed_normals", "sa_lookup_packed_factored", "sa_lookup_backward", "sa_pyramid_backward", "sa_volume_softargmax", "sa_volume_entropy_conf",
 ]
 
 
@@ -96,6 +98,12 @@ def load():
                 f"stereoanywhere_b200: CUDA library {LIB_PATH} is missing and could not be built ({e}). "
                 "There is no CPU fallback; run `python -m stereoanywhere_b200.build`."
             ) from e
+        # an existing library is only acceptable when it was built from exactly these sources (box without nvcc);
+        # a failed rebuild of EDITED sources must not fall back to kernels that no longer match them
+        if not _build.is_current():
+            raise SaError(
+                f"stereoanywhere_b200: {LIB_PATH} was built from different sources than csrc/ and the rebuild "
+                f"failed ({e}); fix the build or run `python -m stereoanywhere_b200.build --force`") from e
     try:
         lib = C.CDLL(LIB_PATH)
         _declare(lib)

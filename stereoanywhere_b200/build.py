@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 OBJDIR = os.path.join(PKG, "build")
 LIB = os.path.join(LIBDIR, "libsa_b200.so")
-SOURCES = ["capi.cu", "lookup.cu", "pyramid.cu", "corr_simt.cu", "corr_tcgen05.cu", "corr_pack_tcgen05.cu", "volume_ops.cu", "packed.cu", "lookup_conv.cu", "volume_reduce.cu", "backward.cu", "volume_rows.cu"]
+SOURCES = ["capi.cu", "lookup.cu", "pyramid.cu", "corr_simt.cu", "corr_tcgen05.cu", "corr_pack_tcgen05.cu", "volume_ops.cu", "packed.cu", "lookup_conv.cu", "volume_reduce.cu", "backward.cu", "volume_rows.cu", "stitch.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
@@ -44,6 +44,12 @@ def _digest() -> str:
             with open(p, "rb") as f:
                 h.update(f.read())
     return h.hexdigest()
+
+
+def is_current() -> bool:
+    """True iff lib/libsa_b200.so exists and its stamp matches the digest of csrc/ + flags."""
+    stamp = os.path.join(LIBDIR, "libsa_b200.stamp")
+    return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == _digest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

@@ -43,6 +43,14 @@ def _needs_grad(*tensors) -> bool:
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
+def _truncate_args(truncate):
+    """(disp, conf, gain) of `truncate=` as the kernels take them: fp32 maps (half-precision maps arrive under
+    autocast), python-float gain."""
+    if truncate is None:
+        return None
+    return (truncate[0].detach().float(), truncate[1].detach().float(), float(truncate[2]))
+
+
 def _no_grad_check(*tensors):
     if _needs_grad(*tensors):
         raise NotImplementedError(
@@ -70,47 +78,59 @@ class _CorrFn(torch.autograd.Function):
         return d2, d3, None, None
 
 
+class _GradState:
+    """What the backward of a block needs, and nothing that points back at the block or its autograd handle (a
+    block -> handle -> grad_fn -> ctx -> block cycle would keep the packed pyramid - 1.47 GB per volume at KITTI
+    size, batch 8 - alive until Python's cyclic GC happens to run)."""
+
+    __slots__ = ("shape", "widths", "truncate", "radius", "pad", "dlevels")
+
+    def __init__(self, shape, widths, truncate, radius, pad):
+        self.shape, self.widths, self.truncate, self.radius, self.pad = shape, list(widths), truncate, radius, list(pad)
+        self.dlevels: Optional[List[torch.Tensor]] = None   # level-gradient accumulators, filled by the lookups' backward
+
+
 class _PyramidFn(torch.autograd.Function):
     """Ties the block to the volume it was built from: returns a 1-element handle; its backward runs after every
-    lookup's backward has accumulated into the block's level-gradient buffers and folds them into dV."""
+    lookup's backward has accumulated into the state's level-gradient buffers and folds them into dV."""
 
     @staticmethod
-    def forward(ctx, fullcorr, block):
-        ctx.block = block
+    def forward(ctx, fullcorr, state):
+        ctx.state = state
         return fullcorr.new_zeros(1)
 
     @staticmethod
     def backward(ctx, _gh):
-        blk = ctx.block
-        b, h, w2, w3 = blk._shape
-        if blk._dlevels is None:  # no lookup took part in the loss
+        st = ctx.state
+        b, h, w2, w3 = st.shape
+        if st.dlevels is None:  # no lookup took part in the loss
             return torch.zeros((b, h, w2, 1, w3), dtype=torch.float32, device=_gh.device), None
-        t = blk._truncate
-        d0 = ops._pyramid_backward(blk._dlevels, blk._widths, t[0] if t else None, t[1] if t else None, t[2] if t else 0.0)
-        blk._dlevels = None
+        t = st.truncate
+        d0 = ops._pyramid_backward(st.dlevels, st.widths, t[0] if t else None, t[1] if t else None, t[2] if t else 0.0)
+        st.dlevels = None
         return d0.view(b, h, w2, 1, w3), None
 
 
 class _LookupFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, handle, coords, block):
-        ctx.block = block
+        ctx.state = block._grad          # not the block: see _GradState
         ctx.save_for_backward(coords)
         return block._lookup_nograd(coords)
 
     @staticmethod
     def backward(ctx, gout):
-        blk = ctx.block
+        st = ctx.state
         (coords,) = ctx.saved_tensors
-        b, h, w2, w3 = blk._shape
-        if blk._dlevels is None:
+        b, h, w2, w3 = st.shape
+        if st.dlevels is None:
             rows = b * h * w2
-            blk._dlevels = [torch.zeros((rows, w3 if i == 0 else ops.level_pitch(w)), dtype=torch.float32, device=gout.device)
-                            for i, w in enumerate(blk._widths)]
-        p0, p1 = blk.pad
+            st.dlevels = [torch.zeros((rows, w3 if i == 0 else ops.level_pitch(w)), dtype=torch.float32, device=gout.device)
+                          for i, w in enumerate(st.widths)]
+        p0, p1 = st.pad
         if p0 or p1:
             gout = torch.nn.functional.pad(gout, (p0, p1))
-        ops._lookup_backward(gout.float(), coords, blk._dlevels, blk._widths, blk.radius, p0)
+        ops._lookup_backward(gout.float(), coords, st.dlevels, st.widths, st.radius, p0)
         return torch.zeros(1, dtype=torch.float32, device=gout.device), None, None
 
 
@@ -132,10 +152,11 @@ class CorrBlockB200:
             fullcorr = fullcorr.contiguous()
         self._reset(num_levels, radius, pad, (b, h, w2, w3))
         grad_src = fullcorr if _needs_grad(fullcorr) else None
-        if grad_src is not None:
-            fullcorr = fullcorr.detach().float()
-        self._src = fullcorr            # the tensor handed in (kept alive like the reference does)
-        self._truncate = None if truncate is None else (truncate[0], truncate[1], float(truncate[2]))
+        # any dtype is accepted, like the reference (bilinear_sampler casts to float and back, utils/utils.py:19-35):
+        # under `--mixed_precision` the hourglass / classifier volumes arrive in fp16 (test.py:63,189)
+        fullcorr = fullcorr.detach().float()
+        self._src = fullcorr            # the volume the lookups see (fp32; the tensor handed in when it already was)
+        self._truncate = _truncate_args(truncate)
         rows = fullcorr.view(b * h * w2, w3)
         if self.layout == "packed" and ops.packable(num_levels, radius, w3, self.pad):
             # one 128-byte line per (pixel, volume) lookup; levels are materialised only on request
@@ -144,7 +165,8 @@ class CorrBlockB200:
         else:
             self._build_levels()
         if grad_src is not None:  # training: lookups go through autograd Functions
-            self._handle = _PyramidFn.apply(grad_src.float() if grad_src.dtype != torch.float32 else grad_src, self)
+            self._grad = _GradState(self._shape, self._widths, self._truncate, self.radius, self.pad)
+            self._handle = _PyramidFn.apply(grad_src.float() if grad_src.dtype != torch.float32 else grad_src, self._grad)
 
     def _reset(self, num_levels: int, radius: int, pad: Sequence[int], shape: Tuple[int, int, int, int]) -> None:
         """Every field of a block, in its empty state; the constructors fill in what they build."""
@@ -159,7 +181,7 @@ class CorrBlockB200:
         self._packed: Optional[torch.Tensor] = None           # line-packed pyramid of the volume
         self._packed_nr: Optional[torch.Tensor] = None        # mono_mode "factored": packed rows of the right normals
         self._otf = False                                     # mono_mode "otf": lookups computed from the normals
-        self._dlevels: Optional[List[torch.Tensor]] = None    # level-gradient accumulators (training only)
+        self._grad: Optional[_GradState] = None               # backward state (training only)
         self._handle: Optional[torch.Tensor] = None           # autograd tie to the volume (training only)
 
     #: "packed" (default; used whenever num_levels=4, radius=4, W3 % 8 == 0, pad=[0,0]) or "levels"
@@ -224,7 +246,7 @@ class CorrBlockB200:
         self = cls.__new__(cls)
         self._reset(num_levels, radius, (0, 0), (b, h, w2, w3))
         self._features = (fmap2.float(), fmap3.float())
-        self._truncate = None if truncate is None else (truncate[0], truncate[1], float(truncate[2]))
+        self._truncate = _truncate_args(truncate)
         t = self._truncate
         self._packed = _OPS.corr_pack(self._features[0], self._features[1], t[0] if t else None, t[1] if t else None,
                                       t[2] if t else 0.0)
@@ -244,8 +266,8 @@ class CorrBlockB200:
             b, h, w2, w3 = self._shape
             rows = self._source().view(b * h * w2, w3)
             t = self._truncate
-            self._levels = list(_OPS.pyramid(rows, self.num_levels, t[0] if t else None, t[1] if t else None,
-                                             t[2] if t else 0.0))
+            self._levels = ops.pyramid_levels(rows, self.num_levels, t[0] if t else None, t[1] if t else None,
+                                              t[2] if t else 0.0)
         return self._levels
 
     @property
@@ -289,13 +311,13 @@ class CorrBlockB200:
     def corr(fmap2: torch.Tensor, fmap3: torch.Tensor) -> torch.Tensor:
         """[B,C,H,W2] x [B,C,H,W3] -> [B,H,W2,1,W3], divided by sqrt(C) (reference corr.py:117-132).
 
-        C % 8 == 0 and 4-aligned widths take the tensor-core kernel in `CorrBlockB200.precision`;
+        C % 32 == 0 (the kernel's channel slab) and 4-aligned widths take the tensor-core kernel in `CorrBlockB200.precision`;
         anything else (the C=3 normals volume in particular) takes the fp32 SIMT kernel."""
         dt = fmap2.dtype
         f2, f3 = fmap2.float(), fmap3.float()
         prec = CorrBlockB200.precision
         c, w2, w3 = f2.shape[1], f2.shape[3], f3.shape[3]
-        if prec != "fp32" and not (c % 8 == 0 and c >= 32 and w2 % 4 == 0 and w3 % 4 == 0 and w3 <= 1024):
+        if prec != "fp32" and not (c % 32 == 0 and w2 % 4 == 0 and w3 % 4 == 0 and w3 <= 1024):
             prec = "fp32"
         if _needs_grad(f2, f3):
             vol = _CorrFn.apply(f2, f3, prec, 1.0)
@@ -313,18 +335,25 @@ class CorrBlockB200:
         return _OPS.corr_volume(n2, n3, "fp32", float(gain))
 
     @staticmethod
+    def _pairable(block_a: "CorrBlockB200", block_b: "CorrBlockB200") -> bool:
+        """Whether `lookup_pair` can serve both blocks from one launch (same geometry, no pad, block_a holding a
+        packed or levels pyramid of its own, neither block under autograd)."""
+        if torch.is_grad_enabled() and (block_a._handle is not None or block_b._handle is not None):
+            return False  # training: each lookup is its own autograd node
+        otf_b = block_b._otf or block_b._packed_nr is not None  # block_b holds no packed volume of its own
+        return not (block_a.radius != block_b.radius or block_a._widths != block_b._widths
+                    or block_a._shape != block_b._shape
+                    or block_a.pad != [0, 0] or block_b.pad != [0, 0] or block_a._otf
+                    or block_a._packed_nr is not None
+                    or (block_a._packed is None) != (block_b._packed is None and not otf_b))
+
+    @staticmethod
     def lookup_pair(block_a: "CorrBlockB200", block_b: "CorrBlockB200", coords: torch.Tensor):
         """`(block_a(coords), block_b(coords))` with one launch (stereoanywhere.py:270-271)."""
         _no_grad_check(coords)
-        if torch.is_grad_enabled() and (block_a._handle is not None or block_b._handle is not None):
-            return block_a(coords), block_b(coords)  # training: each lookup is its own autograd node
+        if not CorrBlockB200._pairable(block_a, block_b):
+            return CorrBlockB200.__call__(block_a, coords), CorrBlockB200.__call__(block_b, coords)
         fact_b = block_b._packed_nr is not None
-        otf_b = block_b._otf or fact_b  # block_b holds no packed volume of its own
-        if (block_a.radius != block_b.radius or block_a._widths != block_b._widths
-                or block_a.pad != [0, 0] or block_b.pad != [0, 0] or block_a._otf
-                or block_a._packed_nr is not None
-                or (block_a._packed is None) != (block_b._packed is None and not otf_b)):
-            return block_a(coords), block_b(coords)
         dt = coords.dtype
         if dt != torch.float32:
             coords = coords.float()

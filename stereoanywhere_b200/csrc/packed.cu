@@ -213,6 +213,7 @@ struct PLookupArgs {
   float divisor, inv_divisor, post_scale;
   // factored mono volume (FV >= 0): packed[FV] holds the packed pyramid of the RIGHT NORMAL MAP's rows,
   // [(b*3 + c)*H + h][nblk][32]; nl / H / Wimg / divisor / inv_divisor / post_scale as above
+  int pf_dist;  // > 0: the idle prologue warp(s) pull the lines of the CTA `pf_dist` launches ahead into L2
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -351,6 +352,30 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
       const float k = blk >= 0 ? a.post_scale * a.inv_divisor : 0.f;
       const int off = blk >= 0 ? (((hw0 + tid) / a.Wimg) * a.nblk + blk) * 32 : 0;
       s_n[tid] = make_float4(n0 * k, n1 * k, n2 * k, __int_as_float(off));
+    }
+  }
+  else if (NV == 2 && a.pf_dist > 0) {
+    // The second half of the CTA has nothing to do in the prologue.  It reads the coordinates of the CTA that
+    // will run `pf_dist` CTAs later and issues an L2 prefetch of that CTA's packed lines: by the time that CTA
+    // stages them they come out of L2 instead of HBM, and the HBM requests of a launch are spread over its whole
+    // duration instead of being issued only by the ~15 % of resident CTAs that are in their staging phase
+    // (the kernel is latency-bound: DRAM ~30 % busy).  No registers held, no dependence on the result.
+    const int t = tid - TILE;
+    const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + a.pf_dist;
+    if (lin < (long long)gridDim.x * gridDim.y) {
+      const int pb = (int)(lin / gridDim.x);
+      const int phw = (int)(lin - (long long)pb * gridDim.x) * TILE + t;
+      if (phw < a.HW) {
+        const float x = __ldg(a.coords + (long long)pb * a.coords_bstride + phw);
+        const float fl = fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
+        const int q = ((int)fl >> 3) - kQMin;
+        if (q >= 0 && q < a.nblk) {
+          const long long off = (((long long)pb * a.HW + phw) * a.nblk + q) * 32;
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+            if (v != OTF && v != FV) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.packed[v] + off));
+        }
+      }
     }
   }
   __syncthreads();
@@ -532,7 +557,10 @@ static int launch_packed_t(const PLookupArgs& a, int B, cudaStream_t st) {
 }
 
 template <int NV, int OTF, int FV = -1>
-static int launch_packed(const PLookupArgs& a, int B, cudaStream_t st) {
+static int launch_packed(PLookupArgs a, int B, cudaStream_t st) {
+  // L2 prefetch distance in CTAs (0 = off); SA_B200_LOOKUP_PF overrides
+  static const int pf = getenv("SA_B200_LOOKUP_PF") ? atoi(getenv("SA_B200_LOOKUP_PF")) : 0;
+  a.pf_dist = pf;
   // (factored mono volume: 32 - 23.5 us against 24.4 at 64 and 27.3 at 128; its staging is latency-bound)
   static const int tile = getenv("SA_B200_LOOKUP_TILE") ? atoi(getenv("SA_B200_LOOKUP_TILE")) : (FV >= 0 ? 32 : 64);
   // pixels per CTA: 64 measured best at c2 (23.2 us per dual lookup; 128: 24.2, 32: 23.5) - smaller CTAs

@@ -361,47 +361,3 @@ int launch_corrupt_rows(const float* vol, const float* bin_mask, int mode, int s
 }
 
 }  // namespace sa
-
-// ---------------------------------------------------------------------------------------------------------
-// Stitch of tile-sharded inference over peer memory: dst[i] = (sum_k srcs[k][i]) / den[i].
-// srcs are the per-rank accumulators `sum disp * w` (reference mapreduce_v2/tile_wrapper.py:340-362) of ALL ranks,
-// addressed through NVLink peer pointers (torch symmetric memory); every rank reduces its own 1/N slice of the
-// plane, normalises it by the weight plane (tile_wrapper.py:185) and stores it straight into rank 0's output:
-// reduce + normalise + gather in one pass over NVSwitch, without an SM-resident collective spinning next to the
-// persistent GEMM kernels.  den == NULL: plain sum.
-namespace sa {
-struct PeerSrcs {
-  const float* p[16];
-};
-__global__ void __launch_bounds__(256) peer_reduce_kernel(const PeerSrcs s, int n_src, const float* __restrict__ den,
-                                                          float* __restrict__ dst, long long n4) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 acc = reinterpret_cast<const float4*>(s.p[0])[i];
-    for (int k = 1; k < n_src; ++k) {
-      const float4 v = reinterpret_cast<const float4*>(s.p[k])[i];
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
-    if (den) {
-      const float4 d = reinterpret_cast<const float4*>(den)[i];
-      acc.x /= d.x; acc.y /= d.y; acc.z /= d.z; acc.w /= d.w;
-    }
-    reinterpret_cast<float4*>(dst)[i] = acc;
-  }
-}
-}  // namespace sa
-
-extern "C" int sa_peer_reduce(const float* const* h_srcs, int n_src, const float* den, float* dst, int64_t n, void* stream) {
-  using namespace sa;
-  SA_REQUIRE(h_srcs && dst && n > 0 && n_src >= 1 && n_src <= 16, SA_E_INVALID, "sa_peer_reduce: bad arguments (1 <= n_src <= 16)");
-  SA_REQUIRE(n % 4 == 0 && aligned16(dst) && (!den || aligned16(den)), SA_E_ALIGN, "sa_peer_reduce: n %% 4 and 16-byte alignment required");
-  PeerSrcs s = {};
-  for (int k = 0; k < n_src; ++k) {
-    SA_REQUIRE(h_srcs[k] && aligned16(h_srcs[k]), SA_E_ALIGN, "sa_peer_reduce: source %d null or misaligned", k);
-    s.p[k] = h_srcs[k];
-  }
-  const long long n4 = n / 4;
-  const long long want = (n4 + 255) / 256;
-  const int grid = (int)(want < (long long)num_sms() * 4 ? want : (long long)num_sms() * 4);
-  peer_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(s, n_src, den, dst, n4);
-  return finish_launch("sa_peer_reduce");
-}

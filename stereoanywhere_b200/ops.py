@@ -109,8 +109,9 @@ def _corr_volume(fmap_l: torch.Tensor, fmap_r: torch.Tensor, precision: str, pos
 
 def _pyramid(vol: torch.Tensor, num_levels: int, trunc_disp: Optional[torch.Tensor],
              trunc_conf: Optional[torch.Tensor], trunc_gain: float) -> List[torch.Tensor]:
-    """vol: [rows, W] (contiguous view of the block's volume). Returns levels [rows, pitch_i];
-    level 0 is `vol` itself, or the truncated product when trunc_* are given."""
+    """vol: [rows, W] (contiguous view of the block's volume). Returns the NEW tensors only (a functional op must
+    not return its input): levels 1.. [rows, pitch_i], preceded by the truncated level 0 when trunc_* are given.
+    Without truncation level 0 is `vol` itself - `pyramid_levels` below prepends it."""
     _cuda_f32(vol, "fullcorr")
     _req(vol.dim() == 2 and vol.is_contiguous(), "pyramid expects a contiguous [rows, W] view")
     _req(1 <= num_levels <= MAX_LEVELS, f"num_levels must be in 1..{MAX_LEVELS}")
@@ -137,7 +138,7 @@ def _pyramid(vol: torch.Tensor, num_levels: int, trunc_disp: Optional[torch.Tens
                 rc = lib.sa_truncate(vol.data_ptr(), trunc_disp.data_ptr(), trunc_conf.data_ptr(), trunc_gain,
                                      levels[0].data_ptr(), rows, w2_size, w, st)
                 _lib.check(rc, "sa_truncate")
-            return levels
+            return levels if trunc else []
         src, src_w, src_pitch = vol, w, w
         nxt = 1
         first = True
@@ -159,7 +160,14 @@ def _pyramid(vol: torch.Tensor, num_levels: int, trunc_disp: Optional[torch.Tens
             nxt += n_out
             src, src_w, src_pitch = outs[-1], widths[nxt - 1], outs[-1].shape[1]
             first = False
-    return levels
+    return levels if trunc else levels[1:]
+
+
+def pyramid_levels(vol: torch.Tensor, num_levels: int, trunc_disp: Optional[torch.Tensor],
+                   trunc_conf: Optional[torch.Tensor], trunc_gain: float) -> List[torch.Tensor]:
+    """All `num_levels` levels of `vol` ([rows, W]); level 0 is `vol` itself unless a truncation is applied."""
+    new = list(torch.ops.sa_b200.pyramid(vol, num_levels, trunc_disp, trunc_conf, trunc_gain))
+    return new if trunc_disp is not None else [vol] + new
 
 
 def _marshal(levels: Sequence[torch.Tensor], widths: Sequence[int]):

@@ -193,179 +193,175 @@ def gather_batch(local: torch.Tensor, group=None) -> torch.Tensor:
     return torch.cat(parts, dim=0)
 
 
-def plan_images(images: int, world: int):
-    """How `images` full-resolution images are spread over `world` ranks so that a rank only ever holds - and
-    communicates - the planes of its own images.  Returns `ranks_of[j]` (the ranks that share image j; the first
-    one is its leader), or None when neither number divides the other (then every rank takes tiles of every image
-    and the stitch is one global reduce)."""
-    if world >= images and world % images == 0:
-        per = world // images
-        return [list(range(j * per, (j + 1) * per)) for j in range(images)]
-    if images % world == 0:
-        per = images // world
-        return [[j // per] for j in range(images)]
-    return None
+class SlotStitcher:
+    """Stitch of tile-sharded inference WITHOUT a collective (config 4; `csrc/stitch.cu`).
 
+    Every (image, tile) unit owns a slot of `tile_h x tile_w` floats on the gathering rank.  The rank that ran a
+    tile launches ONE kernel (`sa_stitch_tile`: un-pad, scale, blend window, multiplicity) whose stores go straight
+    into that slot - a peer pointer over NVLink / NVSwitch when the tile ran on another GPU (torch symmetric
+    memory).  The gathering rank then runs `sa_stitch_finish` once per step: sum of the covering slots in the
+    reference's enumeration order, divided by the weight plane (which depends on the geometry only and is formed
+    once, locally).  What an NCCL `reduce(sum)` of the `[images, H, W]` accumulator did in round 1 - every rank
+    zeroing, accumulating and shipping the whole 91 MB plane - shrinks to each tile crossing the switch exactly once,
+    as soon as it is finished, and the result no longer depends on how the tiles were sharded (fixed summation
+    order): N ranks return bit for bit what one rank returns.
 
-class ImageStitcher:
-    """Stitch of a tile-sharded step over several images with the least data on the wire (config 4, N ranks).
-
-    A global `reduce(sum)` of the `[images, H, W]` accumulator makes every rank push the whole 91 MB (four
-    Middlebury images) through the ring although it only touched its own tiles.  Here the tiles are sharded BY IMAGE
-    (`plan_images`): the ranks that share an image reduce just that `[H, W]` plane among themselves (a sub-group
-    collective; nothing at all when an image belongs to one rank), its leader divides by the weight plane (geometry
-    only, formed locally) and sends the finished plane to the gathering rank.  Both phases are asynchronous and
-    double-buffered: the sub-group reduce of step k is launched after step k's tiles, its normalise + send when step
-    k+1's tiles have been issued, and everything of parity i is waited for when that buffer comes round again.
+    Synchronisation is two signal-pad flags per parity (double-buffered slots): non-gathering ranks `put_signal`
+    DONE after their last tile of a step and `wait_signal` FREE before they overwrite a parity two steps later; the
+    gathering rank does the mirror image on a side stream, so its own next step computes meanwhile.
     """
 
-    def __init__(self, images: int, height: int, width: int, work, device, group=None, dst: int = 0):
+    DONE, FREE = 0, 2   # signal channels (+ parity)
+
+    def __init__(self, images: int, height: int, width: int, work, device, group=None, dst: int = 0,
+                 timeout_ms: int = 60000, local: bool = False):
+        """`local=True`: a single-process stitcher even when torch.distributed is initialised (every tile runs here;
+        used to check an N-rank result against the one-rank result)."""
         import torch.distributed as dist
-
-        self.dist = dist
-        self.group = group
-        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.dst = dst
-        self.ranks_of = plan_images(images, self.world)
-        if self.ranks_of is None:
-            raise ValueError(f"{images} images cannot be spread over {self.world} ranks image by image")
-        self.images = images
-        self.my_images = [j for j, rk in enumerate(self.ranks_of) if self.rank in rk]
-        self.slot = {j: k for k, j in enumerate(self.my_images)}      # image -> index in my accumulator
-        self.shared = len(self.ranks_of[0]) > 1
-        # every rank creates every sub-group, in the same order (torch.distributed requirement)
-        self.groups = [dist.new_group(rk) if self.shared else None for rk in self.ranks_of]
-        self.lead = [j for j in self.my_images if self.ranks_of[j][0] == self.rank]   # images I finish and send
-        n = max(1, len(self.my_images))
-        self.acc = [torch.zeros(n, height, width, dtype=torch.float32, device=device) for _ in range(2)]
-        self.den = torch.clamp(weight_sum(height, width, work, device=device), min=1e-4) if self.lead else None
-        self.norm = [torch.empty(len(self.lead), height, width, dtype=torch.float32, device=device) for _ in range(2)] \
-            if self.lead else None
-        self.out = torch.zeros(images, height, width, dtype=torch.float32, device=device) if self.rank == dst else None
-        self._reduce = [[], []]   # outstanding sub-group reduces of parity i
-        self._p2p = [[], []]      # outstanding sends / receives of parity i
-        self._stage = [0, 0]      # 0 idle, 1 reduce launched, 2 normalise + send launched
-
-    def units(self, work) -> List:
-        """This rank's (image, tile, multiplicity) units: the tiles of its images, round-robin inside an image."""
-        mine = []
-        for j in self.my_images:
-            rk = self.ranks_of[j]
-            mine += [(j, t, m) for i, (t, m) in enumerate(work) if i % len(rk) == rk.index(self.rank)]
-        return mine
-
-    def buffer(self, i: int) -> torch.Tensor:
-        """Accumulator `[my images, H, W]` of parity i (index with `slot[image]`), free to be overwritten."""
-        self._finish(i)
-        return self.acc[i]
-
-    def launch(self, i: int) -> None:
-        """Step k's tiles have been accumulated into buffer i: start its reduce, and move step k-1 one phase on."""
-        if self.shared:
-            for j in self.my_images:
-                k = self.slot[j]
-                self._reduce[i].append(self.dist.reduce(self.acc[i][k], dst=self.ranks_of[j][0], op=self.dist.ReduceOp.SUM,
-                                                        group=self.groups[j], async_op=True))
-        self._stage[i] = 1
-        if self._stage[i ^ 1] == 1:
-            self._send(i ^ 1)
-
-    def _send(self, i: int) -> None:
-        for w in self._reduce[i]:
-            w.wait()
-        self._reduce[i] = []
-        for n, j in enumerate(self.lead):
-            torch.div(self.acc[i][self.slot[j]], self.den, out=self.norm[i][n])
-            if self.rank == self.dst:
-                self.out[j].copy_(self.norm[i][n])
-            else:
-                self._p2p[i].append(self.dist.isend(self.norm[i][n], dst=self.dst, group=self.group))
-        if self.rank == self.dst:
-            for j, rk in enumerate(self.ranks_of):
-                if rk[0] != self.dst:
-                    self._p2p[i].append(self.dist.irecv(self.out[j], src=rk[0], group=self.group))
-        self._stage[i] = 2
-
-    def _finish(self, i: int) -> None:
-        if self._stage[i] == 1:
-            self._send(i)
-        for w in self._p2p[i]:
-            w.wait()
-        self._p2p[i] = []
-        self._stage[i] = 0
-
-    def drain(self) -> Optional[torch.Tensor]:
-        """Complete everything outstanding (oldest step first); the stitched `[images, H, W]` on the gathering rank."""
-        order = (0, 1) if self._stage[0] >= self._stage[1] else (1, 0)
-        for i in order:
-            self._finish(i)
-        return self.out
-
-
-class PeerStitcher:
-    """Stitch of a tile-sharded step over NVLink peer memory instead of an NCCL reduce (config 4).
-
-    Every rank accumulates `sum disp * w` for its tiles into a SYMMETRIC buffer (torch symmetric memory: the same
-    allocation is mapped into every process of the node).  `reduce_to(dst_rank)` then lets each rank sum its own
-    1/N slice of all N accumulators through peer loads, divide by the weight plane (geometry only, formed locally)
-    and store the slice into `dst_rank`'s output buffer: reduce + normalise + gather in ONE kernel per rank
-    (`sa_peer_reduce`), bracketed by two device-side barriers.  It runs on a side stream, double-buffered, so the
-    next step's tiles compute meanwhile - and unlike an SM-resident NCCL reduce it does not sit on SMs that the
-    persistent GEMM kernels of the next tile expect to own.
-    """
-
-    def __init__(self, images: int, height: int, width: int, den: torch.Tensor, device, group=None):
-        import ctypes as C
-
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm
 
         from . import _lib
 
-        self._C, self._lib = C, _lib.load()
-        self.group = group if group is not None else dist.group.WORLD
-        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
-        self.n = images * height * width
-        assert self.n % 4 == 0
-        self.acc = [symm.empty(images, height, width, dtype=torch.float32, device=device) for _ in range(2)]
-        self.acc_h = [symm.rendezvous(t, self.group) for t in self.acc]
-        self.out = symm.empty(images, height, width, dtype=torch.float32, device=device)
-        self.out_h = symm.rendezvous(self.out, self.group)
-        self.den = den.to(device).float().clamp(min=1e-4).unsqueeze(0).expand(images, height, width).contiguous()
-        per = (self.n // 4 + self.world - 1) // self.world * 4
-        self.lo = min(self.n, self.rank * per)
-        self.hi = min(self.n, self.lo + per)
-        self.side = torch.cuda.Stream(device=device)
-        self.ready = [torch.cuda.Event() for _ in range(2)]
-        self.free = [torch.cuda.Event() for _ in range(2)]
-        for e in self.free:
-            e.record(torch.cuda.current_stream(device))
+        self._lib = _lib.load()
+        self.device = torch.device(device)
+        distributed = dist.is_available() and dist.is_initialized() and not local
+        if local:
+            dst = 0
+        self.group = group if group is not None else (dist.group.WORLD if distributed else None)
+        self.rank = dist.get_rank(self.group) if distributed else 0
+        self.world = dist.get_world_size(self.group) if distributed else 1
+        self.dst, self.timeout_ms = dst, timeout_ms
+        self.images, self.height, self.width = images, height, width
+        if width % 4:
+            raise ValueError("SlotStitcher needs an image width that is a multiple of 4")
+        self.units = [(img, tile, mult) for img in range(images) for (tile, mult) in work]
+        self.offsets, total, rows = [], 0, []
+        for img, (y0, y1, x0, x1), _mult in self.units:
+            if x0 % 4 or (x1 - x0) % 4:
+                raise ValueError(f"tile columns must start and end on multiples of 4 (got x0={x0}, x1={x1})")
+            self.offsets.append(total)
+            rows.append([img, y0, y1, x0, x1, total // 4])
+            total += (y1 - y0) * (x1 - x0)
+        self.slot_floats = total
+        self.hdl = None
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm
 
-    def buffer(self, i: int) -> torch.Tensor:
-        """Accumulator of parity i; waits (on the current stream) until every rank has finished reading it."""
-        torch.cuda.current_stream().wait_event(self.free[i])
-        return self.acc[i]
+            self.slots = symm.empty(2 * total, dtype=torch.float32, device=self.device)
+            self.hdl = symm.rendezvous(self.slots, self.group)
+            self._slot_base = int(self.hdl.buffer_ptrs[dst])
+        else:
+            self.slots = torch.empty(2 * total, dtype=torch.float32, device=self.device)
+            self._slot_base = self.slots.data_ptr()
+        self._weights = {}
+        self._step = 0
+        self._parity = 0
+        self._need_free = [False, False]
+        if self.rank == dst:
+            self.den = torch.clamp(weight_sum(height, width, work, device=self.device), min=1e-4)
+            self.table = torch.tensor(rows, dtype=torch.int32, device=self.device)
+            self.out = [torch.empty(images, height, width, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self.side = torch.cuda.Stream(device=self.device)
+            self.tiles_done = [torch.cuda.Event() for _ in range(2)]
+            self.finished = [torch.cuda.Event() for _ in range(2)]
+            for e in self.finished:
+                e.record(torch.cuda.current_stream(self.device))
 
-    def reduce_to(self, i: int, dst_rank: int = 0) -> None:
-        main = torch.cuda.current_stream()
-        self.ready[i].record(main)
+    def my_units(self, rank: Optional[int] = None, world: Optional[int] = None) -> List[int]:
+        """Indices into `self.units` of the tiles `rank` runs (round-robin)."""
+        rank = self.rank if rank is None else rank
+        world = self.world if world is None else world
+        return [i for i in range(len(self.units)) if i % world == rank]
+
+    def begin(self) -> None:
+        """Start a step: pick the slot parity and wait until the gathering rank has finished reading it."""
+        i = self._parity = self._step & 1
+        self._step += 1
+        if self.rank == self.dst:
+            torch.cuda.current_stream(self.device).wait_event(self.finished[i])
+        elif self._need_free[i]:
+            self.hdl.wait_signal(self.dst, self.FREE + i, self.timeout_ms)
+            self._need_free[i] = False
+
+    def add(self, unit: int, src: torch.Tensor, up: int = 1, scale: float = -1.0, pad_top: int = 0, pad_left: int = 0) -> None:
+        """Weighted tile of unit `unit` -> its slot on the gathering rank.  `src`: the tile's result `[..., h, w]`
+        (contiguous fp32): padded full-resolution model output (`up=1, scale=-1`: the reference negates it,
+        tile_wrapper.py:206) or a quarter-resolution disparity (`up=4, scale=4`)."""
+        _img, (y0, y1, x0, x1), mult = self.units[unit]
+        th, tw = y1 - y0, x1 - x0
+        if (th, tw) not in self._weights:
+            self._weights[(th, tw)] = blend_weight(th, tw, device=self.device).contiguous()
+        if src.dtype != torch.float32 or not src.is_contiguous():
+            src = src.float().contiguous()
+        slot = self._slot_base + 4 * (self._parity * self.slot_floats + self.offsets[unit])
+        rc = self._lib.sa_stitch_tile(src.data_ptr(), src.shape[-2], src.shape[-1], up, float(scale), pad_top, pad_left,
+                                      th, tw, self._weights[(th, tw)].data_ptr(), float(mult), slot,
+                                      torch.cuda.current_stream(self.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError("sa_stitch_tile: " + self._lib.sa_last_error().decode())
+
+    def end(self) -> None:
+        """All tiles of this rank's share have been added: signal the gathering rank / finish the image there."""
+        i = self._parity
+        if self.rank != self.dst:
+            self.hdl.put_signal(self.dst, self.DONE + i, self.timeout_ms)
+            self._need_free[i] = True
+            return
+        main = torch.cuda.current_stream(self.device)
+        self.tiles_done[i].record(main)
         with torch.cuda.stream(self.side):
-            self.side.wait_event(self.ready[i])
-            self.acc_h[i].barrier(channel=0)          # every rank's accumulator i is complete
-            if self.hi > self.lo:
-                C = self._C
-                ptrs = (C.c_void_p * self.world)(*[int(p) + 4 * self.lo for p in self.acc_h[i].buffer_ptrs])
-                dst = int(self.out_h.buffer_ptrs[dst_rank]) + 4 * self.lo
-                rc = self._lib.sa_peer_reduce(ptrs, self.world, self.den.data_ptr() + 4 * self.lo, dst, self.hi - self.lo,
-                                              self.side.cuda_stream)
-                if rc != 0:
-                    raise RuntimeError("sa_peer_reduce: " + self._lib.sa_last_error().decode())
-            self.out_h.barrier(channel=1)             # all slices stored, all peer reads of accumulator i done
-            self.free[i].record(self.side)
+            self.side.wait_event(self.tiles_done[i])
+            for r in range(self.world):
+                if r != self.dst:
+                    self.hdl.wait_signal(r, self.DONE + i, self.timeout_ms)
+            rc = self._lib.sa_stitch_finish(self._slot_base + 4 * i * self.slot_floats, self.table.data_ptr(), len(self.units),
+                                            self.den.data_ptr(), self.out[i].data_ptr(), self.images, self.height,
+                                            self.width, self.side.cuda_stream)
+            if rc != 0:
+                raise RuntimeError("sa_stitch_finish: " + self._lib.sa_last_error().decode())
+            for r in range(self.world):
+                if r != self.dst:
+                    self.hdl.put_signal(r, self.FREE + i, self.timeout_ms)
+            self.finished[i].record(self.side)
 
-    def result(self) -> torch.Tensor:
-        """The stitched images on the gathering rank (valid after the side stream has been waited for)."""
-        return self.out
+    def drain(self) -> Optional[torch.Tensor]:
+        """Complete everything outstanding; the stitched `[images, H, W]` of the last step on the gathering rank."""
+        if self.rank == self.dst:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+            return self.out[self._parity] if self._step else None
+        for i in range(2):
+            if self._need_free[i]:
+                self.hdl.wait_signal(self.dst, self.FREE + i, self.timeout_ms)
+                self._need_free[i] = False
+        return None
 
-    def drain(self) -> None:
-        torch.cuda.current_stream().wait_stream(self.side)
+
+def tiled_inference_b200(model: Callable[..., torch.Tensor], left: torch.Tensor, right: torch.Tensor,
+                         mono_left: Optional[torch.Tensor], mono_right: Optional[torch.Tensor], tile_h: int, tile_w: int,
+                         overlap: int, *, stitcher: Optional[SlotStitcher] = None, group=None,
+                         dst: int = 0) -> Optional[torch.Tensor]:
+    """`tiled_inference` on CUDA with the collective-free stitch (`SlotStitcher`): the distinct tiles of the
+    reference's enumeration are sharded over the ranks, each tile's (negated, un-padded, blended) result is stored
+    straight into the gathering rank's memory, and that rank returns the stitched `[1,1,H,W]` disparity - the
+    reference's `TileWrapper.forward` result (tile_wrapper.py:143-187) up to fp32 summation order of repeated
+    tiles.  Pass a `stitcher` to reuse its buffers across calls (same image size and preset)."""
+    b, _, height, width = left.shape
+    if b != 1:
+        raise ValueError("tiled inference supports batch size == 1 (tile_wrapper.py:148-149)")
+    if height <= tile_h and width <= tile_w:
+        return tiled_inference(model, left, right, mono_left, mono_right, tile_h, tile_w, overlap, group=group, dst=dst)
+    if stitcher is None:
+        work = tile_multiplicity(height, width, tile_h, tile_w, overlap)
+        stitcher = SlotStitcher(1, height, width, work, left.device, group=group, dst=dst)
+    stitcher.begin()
+    for u in stitcher.my_units():
+        _img, (y0, y1, x0, x1), _m = stitcher.units[u]
+        pad = pad_to_32(y1 - y0, x1 - x0)
+        args = [None if t is None else F.pad(t[:, :, y0:y1, x0:x1], pad, mode="replicate")
+                for t in (left, right, mono_left, mono_right)]
+        out = model(*args)
+        if isinstance(out, (tuple, list)):
+            out = out[0]
+        stitcher.add(u, out, up=1, scale=-1.0, pad_top=pad[2], pad_left=pad[0])
+    stitcher.end()
+    res = stitcher.drain()
+    return None if res is None else res.view(1, 1, height, width).clone()

@@ -87,27 +87,43 @@ def test_streams_are_respected(lib):
     assert torch.allclose(out, 2.0 * ref, atol=1e-6)
 
 
-def test_peer_reduce_local_pointers():
-    """sa_peer_reduce on one GPU (the pointers of a multi-GPU run are NVLink peer pointers of the same kind)."""
-    import ctypes as C
-
+def test_stitch_kernels_match_the_reference_tile_wrapper(golden_tiles):
+    """sa_stitch_tile + sa_stitch_finish (through `tiling.tiled_inference_b200`, one GPU: local slot pointers - the
+    pointers of a multi-GPU run are NVLink peer pointers of the same kind) against the stitched output of the
+    reference's real `TileWrapper` around a toy model (tests/golden/tiles.npz), and against the host
+    implementation `tiling.tiled_inference`."""
     import torch
 
-    from stereoanywhere_b200 import _lib
+    from stereoanywhere_b200 import tiling
 
-    lib = _lib.load()
-    gen = torch.Generator(device="cuda:0").manual_seed(3)
-    srcs = [torch.randn(4096, device="cuda:0", generator=gen) for _ in range(5)]
-    den = torch.rand(4096, device="cuda:0", generator=gen) + 0.5
-    dst = torch.empty(4096, device="cuda:0")
-    ptrs = (C.c_void_p * 5)(*[t.data_ptr() for t in srcs])
+    g = golden_tiles
+    dev = "cuda:0"
+    l, r, ml, mr = (torch.from_numpy(g[k]).to(dev) for k in ("st_l", "st_r", "st_ml", "st_mr"))
+    th, tw, ov = (int(v) for v in g["st_args"])
+
+    def toy(l_, r_, ml_, mr_):
+        d = (l_.mean(1, keepdim=True) - r_.mean(1, keepdim=True)) * 10 + ml_ * 3 + 0.01 * l_.shape[-1]
+        return -(d + 0.1 * torch.tanh(mr_)), None
+
+    # 220 columns, tiles of 96 with stride 72: x0 = 0, 72, 124 - multiples of 4, as the slot stitch requires
+    out = tiling.tiled_inference_b200(toy, l, r, ml, mr, th, tw, ov)
+    host = tiling.tiled_inference(toy, l, r, ml, mr, th, tw, ov, unique=True)
+    assert out.shape == (1, 1, 150, 220)
+    assert float((out.cpu() - torch.from_numpy(g["st_out"])).abs().max()) < 1e-5
+    assert float((out - host).abs().max()) < 1e-5
+    # a reused stitcher (double-buffered slots, several steps) returns the same image every step
+    work = tiling.tile_multiplicity(150, 220, th, tw, ov)
+    st = tiling.SlotStitcher(1, 150, 220, work, dev)
+    for _ in range(5):
+        again = tiling.tiled_inference_b200(toy, l, r, ml, mr, th, tw, ov, stitcher=st)
+        assert torch.equal(again, out)
+
+
+def test_stitch_error_codes(lib):
+    import torch
+
+    t = torch.zeros(64, 64, device="cuda:0")
     st = torch.cuda.current_stream().cuda_stream
-    assert lib.sa_peer_reduce(ptrs, 5, den.data_ptr(), dst.data_ptr(), 4096, st) == 0
-    want = srcs[0].clone()
-    for t in srcs[1:]:
-        want += t
-    assert torch.equal(dst, want / den)
-    assert lib.sa_peer_reduce(ptrs, 5, None, dst.data_ptr(), 4096, st) == 0
-    assert torch.equal(dst, want)
-    assert lib.sa_peer_reduce(ptrs, 17, None, dst.data_ptr(), 4096, st) == -1   # more than 16 sources
-    assert lib.sa_peer_reduce(ptrs, 5, None, dst.data_ptr(), 4098, st) == -2    # n % 4
+    assert lib.sa_stitch_tile(t.data_ptr(), 64, 64, 1, -1.0, 0, 0, 32, 30, t.data_ptr(), 1.0, t.data_ptr(), st) == -3  # tw % 4
+    assert lib.sa_stitch_tile(t.data_ptr(), 64, 64, 1, -1.0, 40, 0, 32, 32, t.data_ptr(), 1.0, t.data_ptr(), st) == -1  # does not fit
+    assert lib.sa_stitch_tile(None, 64, 64, 1, -1.0, 0, 0, 32, 32, t.data_ptr(), 1.0, t.data_ptr(), st) == -1

@@ -1,0 +1,195 @@
+"""The north star's end-to-end gate with the REAL model: "final disparity within 0.05 px after 32 iterations".
+
+The unmodified reference (`StereoAnywhere.forward`, stereoanywhere.py:95-299, with its own update block,
+update.py:80-90,134-197) runs on the B200 twice on the same seeded inputs and random-init weights (SURVEY 8d,
+end-to-end inputs): once with its own `CorrBlock1D` (einsum + avg_pool2d + grid_sample, executed by ATen on the
+GPU), once with the B200 block put in place by `stereoanywhere_b200.integration.install` - no edit of the
+reference tree.  The reference files travel to the GPU box in the git-ignored
+`oracle/_ref/` (`oracle/make_ref.py`, run by `__graft_entry__.build()`).
+
+Variants:
+  protocol            - `CorrBlock1D := CorrBlockB200`, the reference's call sequence op for op;
+  fused               - lazy `corr()` / truncation: `from_features` (+ dense mono block from the hourglass output),
+                        both lookups of an iteration in one `lookup_pair` launch;
+  fused, raw mono vol - `use_aggregate_mono_vol=False`: `from_features` + `from_normals` (factored) +
+                        `lookup_pair` = exactly the path `bench.py` times.
+"""
+import random
+
+import pytest
+import torch
+
+from oracle import ref_shim
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GATE_PX = 0.05
+
+
+def _reference():
+    if not ref_shim.reference_available():
+        pytest.skip("reference files not found (neither /root/reference nor the prebuilt oracle/_ref): "
+                    "run `python oracle/make_ref.py` in the build container")
+    pkg = ref_shim.import_reference()
+    import importlib
+
+    return pkg, importlib.import_module("models.stereoanywhere.stereoanywhere")
+
+
+def _inputs(h, w, b=1):
+    g = torch.Generator().manual_seed(1)
+    im2 = torch.rand(b, 3, h, w, generator=g)
+    im3 = torch.roll(im2, -8, dims=3)
+    ramp = torch.linspace(0.3, 0.8, w).view(1, 1, 1, w).expand(b, 1, h, w).contiguous()
+    mde2, mde3 = ramp, torch.roll(ramp, -8, dims=3)
+    return [t.to(DEV) for t in (im2, im3, mde2, mde3)]
+
+
+def _forward(model, inputs, iters=32):
+    random.seed(0)   # the forward draws random.random() six times even in test mode (stereoanywhere.py:218-248)
+    with torch.no_grad():
+        disp, _ = model(*inputs, iters=iters, test_mode=True)
+    torch.cuda.synchronize()
+    return disp
+
+
+class _Count:
+    """Counts calls of the entry points the fused wiring is supposed to take (the test must not pass on a path that
+    silently materialised everything)."""
+
+    def __init__(self, B):
+        self.B, self.n = B, {"from_features": 0, "from_normals": 0, "lookup_pair": 0}
+        self.saved = {k: B.__dict__[k] for k in self.n}
+
+    def __enter__(self):
+        B = self.B
+        for name in self.n:
+            fn = getattr(B, name)
+
+            def wrap(*a, _fn=fn, _name=name, **k):
+                self.n[_name] += 1
+                return _fn(*a, **k)
+
+            setattr(B, name, staticmethod(wrap))
+        return self
+
+    def __exit__(self, *exc):
+        for name, orig in self.saved.items():
+            setattr(self.B, name, orig)
+        return False
+
+
+@pytest.mark.parametrize("variant,model_args,h,w", [
+    ("protocol", {}, 384, 512),
+    ("fused", {}, 384, 512),
+    ("fused", {"use_aggregate_mono_vol": False}, 384, 512),
+    ("protocol", {"use_aggregate_mono_vol": False}, 384, 512),
+    ("fused", {"use_aggregate_mono_vol": False}, 384, 1248),     # KITTI size after the /32 pad (W/4 = 312)
+])
+def test_real_model_epe_after_32_iterations(variant, model_args, h, w):
+    import stereoanywhere_b200 as sa
+    from stereoanywhere_b200 import integration
+
+    pkg, sa_mod = _reference()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    torch.manual_seed(0)
+    model = pkg.StereoAnywhere(dict(model_args)).to(DEV).eval()
+    inputs = _inputs(h, w)
+    B = sa.CorrBlockB200
+    assert B.precision == "tf32" and B.mono_mode == "factored"
+
+    integration.uninstall(sa_mod)
+    assert sa_mod.CorrBlock1D.__module__.startswith("models.stereoanywhere")   # the reference's own block
+    d_ref = _forward(model, inputs)
+    d_ref2 = _forward(model, inputs)           # run-to-run noise floor of the reference itself on this GPU
+    try:
+        integration.install(sa_mod, fused=(variant == "fused"))
+        with _Count(B) as cnt:
+            d_b200 = _forward(model, inputs)
+    finally:
+        integration.uninstall(sa_mod)
+
+    assert torch.isfinite(d_ref).all() and torch.isfinite(d_b200).all()
+    epe = float((d_b200 - d_ref).abs().mean())
+    worst = float((d_b200 - d_ref).abs().max())
+    floor = float((d_ref2 - d_ref).abs().max())
+    print(f"[{variant} {model_args} {h}x{w}] EPE {epe:.2e} px (max {worst:.2e}); reference run-to-run max {floor:.2e}; "
+          f"mean |disp| {float(d_ref.abs().mean()):.3f} px; calls {cnt.n}")
+    assert float(d_ref.abs().mean()) > 1e-2, "the model predicted ~0 everywhere: the comparison would be vacuous"
+    if variant == "fused":
+        assert cnt.n["from_features"] == 1 and cnt.n["lookup_pair"] == 32, cnt.n
+        assert cnt.n["from_normals"] == (1 if model_args.get("use_aggregate_mono_vol") is False else 0), cnt.n
+    assert epe < GATE_PX, f"EPE {epe} px exceeds the {GATE_PX} px gate"
+
+
+def test_half_precision_volume_and_maps():
+    """Under the reference's --mixed_precision autocast (test.py:63,189) the hourglass / classifier volumes and the
+    truncation maps arrive in fp16; `CorrBlock1D` takes any dtype (bilinear_sampler casts, utils/utils.py:19-35)."""
+    import stereoanywhere_b200 as sa
+
+    B = sa.CorrBlockB200
+    g = torch.Generator(device=DEV).manual_seed(3)
+    b, h, w = 1, 6, 64
+    vol = torch.randn(b, h, w, 1, w, device=DEV, generator=g)
+    x = torch.arange(w, device=DEV, dtype=torch.float32).view(1, 1, 1, w).expand(b, 1, h, w)
+    coords = torch.cat([x - torch.rand(b, 1, h, w, device=DEV, generator=g) * 9, torch.zeros(b, 1, h, w, device=DEV)], 1)
+    disp = torch.rand(b, 1, h, w, device=DEV, generator=g) * 9
+    conf = torch.rand(b, 1, h, w, device=DEV, generator=g)
+    for dt in (torch.float16, torch.bfloat16):
+        out_h = B(vol.to(dt), num_levels=4, radius=4)(coords)
+        out_f = B(vol.to(dt).float(), num_levels=4, radius=4)(coords)
+        assert out_h.dtype == torch.float32 and torch.equal(out_h, out_f)
+        t_h = B(vol, num_levels=4, radius=4, truncate=(disp.to(dt), conf.to(dt), 0.9))(coords)
+        t_f = B(vol, num_levels=4, radius=4, truncate=(disp.to(dt).float(), conf.to(dt).float(), 0.9))(coords)
+        assert torch.equal(t_h, t_f)
+        fl = torch.randn(b, 64, h, w, device=DEV, generator=g)
+        fr = torch.randn(b, 64, h, w, device=DEV, generator=g)
+        f_h = B.from_features(fl, fr, truncate=(disp.to(dt), conf.to(dt), 0.9))(coords)
+        f_f = B.from_features(fl, fr, truncate=(disp.to(dt).float(), conf.to(dt).float(), 0.9))(coords)
+        assert torch.equal(f_h, f_f)
+        assert B(vol, num_levels=4, radius=4)(coords.to(dt)).dtype == dt   # output follows coords.dtype (corr.py:115)
+
+
+def test_training_block_is_freed_by_refcount():
+    """A block built from a volume that requires grad must not sit in a reference cycle (block -> handle -> grad_fn
+    -> ctx -> block): its packed pyramid is >1 GB per volume at KITTI size and nothing triggers Python's cyclic GC on
+    CUDA memory pressure."""
+    import gc
+    import weakref
+
+    import stereoanywhere_b200 as sa
+
+    B = sa.CorrBlockB200
+    gc.collect()
+    gc.disable()
+    try:
+        vol = torch.randn(1, 4, 64, 1, 64, device=DEV, requires_grad=True)
+        x = torch.arange(64, device=DEV, dtype=torch.float32).view(1, 1, 1, 64).expand(1, 1, 4, 64)
+        coords = torch.cat([x - 3.3, torch.zeros(1, 1, 4, 64, device=DEV)], 1)
+        blk = B(vol, num_levels=4, radius=4)
+        packed_ref = weakref.ref(blk._packed)
+        out = blk(coords)
+        out.sum().backward()
+        assert vol.grad is not None and float(vol.grad.abs().sum()) > 0
+        ref = weakref.ref(blk)
+        del blk, out
+        assert ref() is None and packed_ref() is None, "block (or its packed pyramid) survived without a GC pass"
+    finally:
+        gc.enable()
+
+
+def test_corr_channel_counts_off_the_slab():
+    """C = 40, 48 (multiples of 8, not of the tensor-core kernel's 32-channel slab) take the fp32 kernel."""
+    import stereoanywhere_b200 as sa
+
+    B = sa.CorrBlockB200
+    g = torch.Generator(device=DEV).manual_seed(5)
+    for c in (40, 48, 72):
+        fl = torch.randn(1, c, 4, 64, device=DEV, generator=g)
+        fr = torch.randn(1, c, 4, 64, device=DEV, generator=g)
+        vol = B.corr(fl, fr)
+        ref = torch.einsum("aijk,aijh->ajkh", fl.double(), fr.double()) / (c ** 0.5)
+        err = float((vol.squeeze(3).double() - ref).abs().max() / ref.abs().max())
+        assert err < 2e-6, (c, err)

@@ -131,5 +131,70 @@ def test_bench_reference_arm_prints_one_json_line():
     assert out["impl"] == "reference" and out["unit"] == "pairs/s" and out["value"] > 0
     for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
         assert key in out, key
-    assert out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["cores"] >= 1
+    # the reference's own CorrBlock1D is timed whenever its files are there (here: /root/reference or oracle/_ref)
+    from oracle import ref_path
+
+    assert out["cpu_baseline"]["kind"] == ("reference" if ref_path.available() else "port")
+    assert out["cpu_baseline"]["cores"] >= 1 and out["warmup"] == 0
     assert out["e2e"]["h2d_bytes_per_step"] == 0 and out["e2e"]["d2h_bytes_per_step"] == 0
+    # both arms print the same `config` (the driver compares them)
+    import bench
+
+    assert out["config"] == bench.workload_config("c1_384x512_b1", 1)
+
+
+def test_oracle_ref_recipe_and_reference_path():
+    """`oracle/make_ref.py` reproduces the reference files byte for byte (the copy that travels to the GPU box), and
+    the path run by the reference's own classes equals the oracle's restatement bit for bit."""
+    import torch
+
+    from oracle import corr_oracle as O
+    from oracle import make_ref, ref_path
+
+    if not ref_path.available():
+        pytest.skip("no reference files in this environment")
+    if os.path.isdir("/root/reference/models/stereoanywhere"):
+        assert make_ref.make() and make_ref.verify()
+        import json
+
+        files = json.load(open(os.path.join(make_ref.DEST, "MANIFEST.json")))["files"]
+        assert "models/stereoanywhere/corr.py" in files and "mapreduce_v2/tile_wrapper.py" in files
+        for rel in files:
+            assert open(os.path.join("/root/reference", rel), "rb").read() == open(os.path.join(make_ref.DEST, rel), "rb").read()
+    g = torch.Generator().manual_seed(11)
+    b, c, h, w = 1, 16, 3, 40
+    fl, fr = torch.randn(b, c, h, w, generator=g), torch.randn(b, c, h, w, generator=g)
+    nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w, generator=g), dim=1)
+    nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w, generator=g), dim=1)
+    x = torch.arange(w, dtype=torch.float32).view(1, 1, 1, w).expand(b, 1, h, w)
+    coords = [torch.cat([x - torch.rand(b, 1, h, w, generator=g) * 10, torch.zeros(b, 1, h, w)], 1) for _ in range(2)]
+    trunc = (torch.rand(b, 1, h, w, generator=g) * 10, torch.rand(b, 1, h, w, generator=g), 0.9)
+    rs, rm = ref_path.run_path_reference(fl, fr, nl, nr, coords, trunc=trunc)
+    ps, pm = O.run_path_cpu(fl, fr, nl, nr, coords, trunc=trunc)
+    assert torch.equal(rs, ps) and torch.equal(rm, pm)
+
+
+def test_integration_install_uninstall_swaps_the_reference_names():
+    """`integration.install` only rebinds two names of the reference module and `uninstall` restores them."""
+    import types
+
+    from stereoanywhere_b200 import CorrBlockB200, integration
+
+    mod = types.SimpleNamespace(CorrBlock1D=object(), truncate_corr_volume_v2=lambda *a, **k: "ref")
+    orig = (mod.CorrBlock1D, mod.truncate_corr_volume_v2)
+    integration.install(mod)
+    assert mod.CorrBlock1D is CorrBlockB200 and mod.truncate_corr_volume_v2 is orig[1]
+    integration.install(mod, fused=True)
+    assert mod.CorrBlock1D is integration.FusedCorrBlock and mod.truncate_corr_volume_v2 is not orig[1]
+    import torch
+
+    d = torch.zeros(1, 1, 2, 8)
+    assert mod.truncate_corr_volume_v2(d, d, conf_th=None, attenuation_gain=0.9) == "ref"   # CPU tensors: reference function
+    integration.uninstall(mod)
+    assert (mod.CorrBlock1D, mod.truncate_corr_volume_v2) == orig
+    # the symbolic reshapes of stereoanywhere.py:135-136, 253-258
+    lv = integration.LazyVolume(torch.zeros(2, 3, 4, 8), torch.zeros(2, 3, 4, 16))
+    assert lv.shape == [2, 4, 8, 1, 16]
+    v = (1.73 * lv.squeeze(3).unsqueeze(1))
+    assert v.shape == [2, 1, 4, 8, 16] and abs(v.gain - 1.73) < 1e-12
+    assert v.squeeze(1).unsqueeze(3).shape == [2, 4, 8, 1, 16]

@@ -603,7 +603,7 @@ def run_gpu(args):
                                    "hbm_frac_real_bytes": round(real_px * p / (lk_launch_ms * 1e-3) / 1e9 / peak, 4)},
             }
             roof["kernels"] = kernels   # also inside `roofline`: the driver's parser keeps this object whole
-        cpu = None if args.no_cpu_baseline else cpu_baseline(args.workload, sample_pairs=args.cpu_pairs, reps=3)
+        cpu = None if args.no_cpu_baseline else cpu_baseline(args.workload, sample_pairs=args.cpu_pairs)
         copy_gbs = h2d / (copy_ms * 1e-3) / 1e9
         result = {
             "metric": metric_for(args.workload), "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -669,11 +669,13 @@ def tiled_measure(sa, dev, rank, world, dist, args, steps, warmup):
     def tile_path(d):
         fs = B.from_features(d["fl"], d["fr"], radius=RADIUS, num_levels=LEVELS, truncate=(d["tdisp"], d["tconf"], 0.9))
         fm = B.from_normals(d["nl"], d["nr"], radius=RADIUS, num_levels=LEVELS)
-        coords = d["coords0"]
-        for _ in range(ITERS):
-            B.lookup_pair(fs, fm, coords)
-            coords = coords + d["delta"]
-        return (d["coords0"] - coords)[:, :1].contiguous()   # quarter-resolution disparity, positive
+        # coords of the 32 iterations formed up front, as in the batch workloads (GpuPath.coords_seq): in the model
+        # they come out of the update block, which is out of scope
+        k = torch.arange(ITERS + 1, device=dev, dtype=torch.float32).view(ITERS + 1, 1, 1, 1, 1)
+        seq = d["coords0"].unsqueeze(0) + k * d["delta"].unsqueeze(0)
+        for i in range(ITERS):
+            B.lookup_pair(fs, fm, seq[i])
+        return (d["coords0"] - seq[ITERS])[:, :1].contiguous()   # quarter-resolution disparity, positive
 
     pool = [None]
     runners = {}
@@ -857,8 +859,9 @@ def cpu_once(workload, pairs, fn):
     return time.perf_counter() - t0, pairs
 
 
-def cpu_baseline(workload, sample_pairs=8, reps=3, min_seconds=10.0):
-    """Bounded CPU sample: whole batches of the workload until >= min_seconds of work (>= reps batches)."""
+def cpu_baseline(workload, sample_pairs=8, reps=2, min_seconds=10.0):
+    """Bounded CPU sample: whole batches of the workload until >= min_seconds of work (>= reps batches; the
+    reference's own block needs ~11 s per KITTI-size batch of 8 on 16 cores: 2 batches)."""
     torch.set_num_threads(os.cpu_count() or 1)
     fn, kind, what = cpu_runner()
     cpu_once(workload, 1, fn)  # warm-up (thread pool, allocator)

@@ -46,6 +46,10 @@ const char* sa_last_error(void);
  * stereoanywhere.py:136 (post_scale).  fmap_l is [B,C,H,W2], fmap_r is [B,C,H,W3], both
  * contiguous fp32; vol is rows = B*H*W2 by W3 floats, contiguous.
  *
+ * divisor > 0: correctly rounded division (the reference on the CPU).  divisor < 0: vol = acc * (1.0f / |divisor|) -
+ * what the reference computes on a CUDA device, where ATen multiplies by the fp32 reciprocal of a scalar divisor
+ * (one ulp apart for sqrt(3), identical for sqrt(256)).  The same convention holds for every `divisor` below.
+ *
  * sa_corr_fp32  : SIMT fp32 FMA, any C >= 1 (the mono C=3 volume is a pure streaming write).
  * sa_corr_tf32  : tcgen05 kind::tf32, operands TMA-staged straight from NCHW (MN-major), fp32
  *                 accumulate in TMEM.  Needs C % 8 == 0, W2 % 4 == 0, W3 % 4 == 0, W3 <= 1024,

@@ -289,7 +289,7 @@ extern "C" int sa_corr_pack_tf32(const float* fmap_l, const float* fmap_r, int B
 
   Args a = {};
   a.C = C; a.H = H; a.W2 = W2; a.W3 = W3;
-  a.scale = (float)(1.0 / (double)divisor) * post_scale;
+  a.scale = kernel_inv_divisor(divisor) * post_scale;
   a.m_tiles = (W2 + kBM - 1) / kBM;
   a.nch = (W3 + kBox - 1) / kBox;
   a.n_tiles = (a.nch + 7) / 8;

@@ -104,6 +104,6 @@ extern "C" int sa_corr_fp32(const float* fmap_l, const float* fmap_r, float* vol
   const long long blocks = (long long)B * H * tiles_m * tiles_n;
   SA_REQUIRE(blocks < (1ll << 31), SA_E_UNSUPPORTED, "sa_corr_fp32: too many tiles");
   corr_simt_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(fmap_l, fmap_r, vol, C, H, W2, W3, tiles_m,
-                                                                      tiles_n, divisor, (float)(1.0 / (double)divisor), post_scale);
+                                                                      tiles_n, kernel_divisor(divisor), kernel_inv_divisor(divisor), post_scale);
   return finish_launch("sa_corr_fp32");
 }

@@ -249,7 +249,7 @@ extern "C" int sa_corr_tf32(const float* fmap_l, const float* fmap_r, float* vol
 
   CorrTcArgs a = {};
   a.C = C; a.H = H; a.W2 = W2; a.W3 = W3;
-  a.inv_divisor = (float)(1.0 / (double)divisor); a.post_scale = post_scale;
+  a.inv_divisor = kernel_inv_divisor(divisor); a.post_scale = post_scale;
   a.m_tiles = (W2 + kBM - 1) / kBM;
   a.n_tiles = (W3 + 255) / 256;
   const int per = (W3 + a.n_tiles - 1) / a.n_tiles;

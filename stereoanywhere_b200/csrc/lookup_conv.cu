@@ -383,6 +383,6 @@ extern "C" int sa_lookup_factored_conv(const float* packed_a, const float* packe
   a.nblk = W3 / 8 + 9;
   a.B = B;
   a.nl = normals_l; a.H = H; a.Wimg = W;
-  a.kscale = post_scale * (float)(1.0 / (double)divisor);
+  a.kscale = post_scale * kernel_inv_divisor(divisor);
   return launch_lookup_conv<true>(a, (cudaStream_t)stream, "sa_lookup_factored_conv");
 }

@@ -620,7 +620,7 @@ extern "C" int sa_pack_pyramid_normals(const float* normals_l, const float* norm
   SA_REQUIRE(aligned16(normals_r) && aligned16(packed), SA_E_ALIGN, "sa_pack_pyramid_normals: pointers must be 16-byte aligned");
   PackArgs a = {};
   a.nl = normals_l; a.nr = normals_r; a.H = H; a.W2 = W2;
-  a.divisor = divisor; a.inv_divisor = (float)(1.0 / (double)divisor); a.post_scale = post_scale;
+  a.divisor = kernel_divisor(divisor); a.inv_divisor = kernel_inv_divisor(divisor); a.post_scale = post_scale;
   a.packed = packed; a.rows = (long long)B * H * W2; a.W = W3;
   return launch_pack(a, false, true, (cudaStream_t)stream);
 }
@@ -659,7 +659,7 @@ extern "C" int sa_lookup_packed_normals(const float* packed_a, const float* norm
   a.coords = coords; a.coords_bstride = coords_bstride;
   a.HW = H * W; a.W3 = W3; a.nblk = packed_blocks(W3);
   a.nl = normals_l; a.nr = normals_r; a.H = H; a.Wimg = W;
-  a.divisor = divisor; a.inv_divisor = (float)(1.0 / (double)divisor); a.post_scale = post_scale;
+  a.divisor = kernel_divisor(divisor); a.inv_divisor = kernel_inv_divisor(divisor); a.post_scale = post_scale;
   if (packed_a) {
     a.packed[0] = packed_a; a.out[0] = out_a; a.out[1] = out_mono;
     return launch_packed<2, 1>(a, B, (cudaStream_t)stream);
@@ -685,7 +685,7 @@ extern "C" int sa_lookup_packed_factored(const float* packed_a, const float* pac
   a.coords = coords; a.coords_bstride = coords_bstride;
   a.HW = H * W; a.W3 = W3; a.nblk = packed_blocks(W3);
   a.nl = normals_l; a.H = H; a.Wimg = W;
-  a.divisor = divisor; a.inv_divisor = (float)(1.0 / (double)divisor); a.post_scale = post_scale;
+  a.divisor = kernel_divisor(divisor); a.inv_divisor = kernel_inv_divisor(divisor); a.post_scale = post_scale;
   if (packed_a) {
     a.packed[0] = packed_a; a.packed[1] = packed_normals_r; a.out[0] = out_a; a.out[1] = out_mono;
     return launch_packed<2, -1, 1>(a, B, (cudaStream_t)stream);

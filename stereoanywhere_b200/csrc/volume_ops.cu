@@ -127,7 +127,7 @@ extern "C" int sa_masked_volume(const float* vol, const float* normals_l, const 
     masked_volume_kernel<false><<<grid, 256, 0, st>>>(vol, nullptr, nullptr, 1.f, 1.f, 1.f, mde_l, mde_r, ed, n_bins, out,
                                                       H, W2, W3, nvec);
   else
-    masked_volume_kernel<true><<<grid, 256, 0, st>>>(nullptr, normals_l, normals_r, divisor, (float)(1.0 / (double)divisor),
+    masked_volume_kernel<true><<<grid, 256, 0, st>>>(nullptr, normals_l, normals_r, kernel_divisor(divisor), kernel_inv_divisor(divisor),
                                                      post_scale, mde_l,
                                                      mde_r, ed, n_bins, out, H, W2, W3, nvec);
   return finish_launch("sa_masked_volume");

@@ -325,8 +325,8 @@ static int rows_grid(long long rows) {
 int launch_mono_volume_rows(const float* nl, const float* nr, float* out, int B, int H, int W2, int W3, float divisor,
                             float post_scale, cudaStream_t st) {
   const long long rows = (long long)B * H * W2;
-  mono_volume_rows_kernel<<<rows_grid(rows), kRowWarps * 32, 0, st>>>(nl, nr, out, H, W2, W3, rows, divisor,
-                                                                       (float)(1.0 / (double)divisor), post_scale);
+  mono_volume_rows_kernel<<<rows_grid(rows), kRowWarps * 32, 0, st>>>(nl, nr, out, H, W2, W3, rows, kernel_divisor(divisor),
+                                                                       kernel_inv_divisor(divisor), post_scale);
   return finish_launch("sa_corr_fp32 (C = 3 rows)");
 }
 
@@ -348,8 +348,8 @@ int launch_masked_volume_rows(const float* vol, const float* nl, const float* nr
     masked_volume_rows_kernel<false><<<rows_grid(rows), kRowWarps * 32, 0, st>>>(vol, nullptr, nullptr, 1.f, 1.f, 1.f, mde_l, mde_r,
                                                                                 ed, n_bins, out, H, W2, W3, rows);
   else
-    masked_volume_rows_kernel<true><<<rows_grid(rows), kRowWarps * 32, 0, st>>>(nullptr, nl, nr, divisor,
-                                                                               (float)(1.0 / (double)divisor), post_scale, mde_l,
+    masked_volume_rows_kernel<true><<<rows_grid(rows), kRowWarps * 32, 0, st>>>(nullptr, nl, nr, kernel_divisor(divisor),
+                                                                               kernel_inv_divisor(divisor), post_scale, mde_l,
                                                                                mde_r, ed, n_bins, out, H, W2, W3, rows);
   return finish_launch("sa_masked_volume (rows)");
 }

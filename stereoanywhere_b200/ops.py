@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -29,6 +30,23 @@ def _stream_ptr(t: torch.Tensor) -> int:
         idx = t.device.index
         return _raw_stream(torch.cuda.current_device() if idx is None else idx)
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+#: How `acc / sqrt(C)` (corr.py:132) is rounded.  "reciprocal": acc * (1.0f / sqrt(C)) - what the reference computes
+#: when it runs ON A CUDA DEVICE (ATen's true-division kernel multiplies by the fp32 reciprocal of a scalar divisor),
+#: so the C = 3 mono volume is bit-identical to the reference's on the same GPU.  "exact": correctly rounded division
+#: - the reference on the CPU (the golden fixtures).  They differ by one ulp in ~1/4 of the entries for sqrt(3) and
+#: not at all for the stereo volume (sqrt(256) = 16).  The one ulp matters: `weighted_lsq` (utils/utils.py:345-384,
+#: out of scope) selects pixels by quantile thresholds and can amplify it to 0.1 px of final disparity.
+DIVISION = os.environ.get("SA_B200_DIVISION", "reciprocal")
+
+
+def _divisor(c: int) -> float:
+    """sqrt(C) as the reference forms it (a float32 scalar, corr.py:132); negative = reciprocal convention of the C ABI."""
+    if DIVISION not in ("reciprocal", "exact"):
+        raise ValueError(f"stereoanywhere_b200.ops.DIVISION must be 'reciprocal' or 'exact' (got {DIVISION!r})")
+    d = float(torch.sqrt(torch.tensor(c)))
+    return -d if DIVISION == "reciprocal" else d
 
 
 def packed_row_floats(w3: int) -> int:
@@ -92,7 +110,7 @@ def _corr_volume(fmap_l: torch.Tensor, fmap_r: torch.Tensor, precision: str, pos
     fmap_r = fmap_r.contiguous()
     vol = torch.empty((b, h, w2, 1, w3), dtype=torch.float32, device=fmap_l.device)
     # the reference divides by torch.sqrt(torch.tensor(C)): a float32 scalar (corr.py:132)
-    divisor = float(torch.sqrt(torch.tensor(c)))
+    divisor = _divisor(c)
     lib = _lib.load()
     with _on(fmap_l.device):
         if precision == "fp32":
@@ -265,7 +283,7 @@ def _pack_pyramid_normals(normals_l: torch.Tensor, normals_r: torch.Tensor, post
     normals_l, normals_r = normals_l.contiguous(), normals_r.contiguous()
     lib = _lib.load()
     packed = torch.empty((b * h * w2, packed_row_floats(w3)), dtype=torch.float32, device=normals_l.device)
-    divisor = float(torch.sqrt(torch.tensor(3)))
+    divisor = _divisor(3)
     with _on(normals_l.device):
         rc = lib.sa_pack_pyramid_normals(normals_l.data_ptr(), normals_r.data_ptr(), divisor, post_scale, b, h, w2, w3,
                                          packed.data_ptr(), _stream_ptr(packed))
@@ -288,7 +306,7 @@ def _corr_pack(fmap_l: torch.Tensor, fmap_r: torch.Tensor, trunc_disp: Optional[
     lib = _lib.load()
     rows = b * h * w2
     packed = torch.empty((rows, packed_row_floats(w3)), dtype=torch.float32, device=fmap_l.device)
-    divisor = float(torch.sqrt(torch.tensor(c)))
+    divisor = _divisor(c)
     td = tc = None
     if trunc_disp is not None:
         _cuda_f32(trunc_disp, "trunc_disp")
@@ -409,7 +427,7 @@ def _lookup_normals(packed_a: Optional[torch.Tensor], normals_l: torch.Tensor, n
         _req(packed_a.shape == (b * h * w, packed_row_floats(w3)), "coords do not match the packed volume")
         out_a = torch.empty_like(out_m)
     lib = _lib.load()
-    divisor = float(torch.sqrt(torch.tensor(3)))
+    divisor = _divisor(3)
     with _on(coords.device):
         rc = lib.sa_lookup_packed_normals(packed_a.data_ptr() if packed_a is not None else None, normals_l.data_ptr(),
                                           normals_r.data_ptr(), divisor, float(post_scale), w3, coords.data_ptr(),
@@ -439,7 +457,7 @@ def _lookup_factored(packed_a: Optional[torch.Tensor], packed_nr: torch.Tensor, 
         _req(packed_a.shape == (b * h * w, packed_row_floats(w3)), "coords do not match the packed volume")
         out_a = torch.empty_like(out_m)
     lib = _lib.load()
-    divisor = float(torch.sqrt(torch.tensor(3)))
+    divisor = _divisor(3)
     with _on(coords.device):
         rc = lib.sa_lookup_packed_factored(packed_a.data_ptr() if packed_a is not None else None, packed_nr.data_ptr(),
                                            normals_l.data_ptr(), divisor, float(post_scale), w3, coords.data_ptr(),
@@ -507,7 +525,7 @@ def _lookup_factored_conv(packed_a: torch.Tensor, packed_nr: torch.Tensor, norma
     out_a = torch.empty((b, 64, h, w), dtype=torch.float32, device=coords.device)
     out_m = torch.empty_like(out_a)
     lib = _lib.load()
-    divisor = float(torch.sqrt(torch.tensor(3)))
+    divisor = _divisor(3)
     with _on(coords.device):
         rc = lib.sa_lookup_factored_conv(packed_a.data_ptr(), packed_nr.data_ptr(), normals_l.data_ptr(), divisor,
                                          float(post_scale), w3, coords.data_ptr(), coords.stride(0), weight.data_ptr(),
@@ -572,7 +590,7 @@ def _masked_volume(vol: Optional[torch.Tensor], normals_l: Optional[torch.Tensor
             _cuda_f32(normals_r, "normals_r")
             _req(normals_l.shape == (b, 3, h, w2) and normals_r.shape == (b, 3, h, w3), "normals must be [B,3,H,W]")
             normals_l, normals_r = normals_l.contiguous(), normals_r.contiguous()
-            divisor = float(torch.sqrt(torch.tensor(3)))
+            divisor = _divisor(3)
             rc = lib.sa_masked_volume(None, normals_l.data_ptr(), normals_r.data_ptr(), divisor, post_scale,
                                       mde_l.data_ptr(), mde_r.data_ptr(), bin_edges(n_bins), n_bins, out.data_ptr(),
                                       b, h, w2, w3, _stream_ptr(out))

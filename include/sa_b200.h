@@ -204,6 +204,15 @@ int sa_volume_entropy_conf(const float* vol, int64_t BH, int W2, int W3, float* 
  *   sa_pyramid_backward  folds the level gradients into level 0 in place: d0 <- [T *] (dP_0 + pooled adjoints);
  *                        with trunc_* the result is the gradient w.r.t. V of the block built from T * V
  *                        (T detached as in the reference, stereoanywhere.py:203). */
+/*   sa_corr_backward_tf32  adjoint of A1 on the tensor cores (corr.py:130-132 under autograd): with G = grad_vol
+ *                        [B,H,W2,W3] and s = post_scale / divisor,
+ *                          grad_l[b,c,h,w2] = s * sum_w3 G[b,h,w2,w3] * fmap_r[b,c,h,w3]
+ *                          grad_r[b,c,h,w3] = s * sum_w2 G[b,h,w2,w3] * fmap_l[b,c,h,w2]
+ *                        (either output may be NULL).  tcgen05 kind::tf32, operands TMA-staged from NCHW (K-major)
+ *                        and from the volume gradient, fp32 accumulate in TMEM; W2 % 4 == 0, W3 % 4 == 0, 16-byte
+ *                        aligned pointers; normwise error <= 1e-3 of max|grad|. */
+int sa_corr_backward_tf32(const float* grad_vol, const float* fmap_l, const float* fmap_r, float* grad_l, float* grad_r,
+                          int B, int C, int H, int W2, int W3, float divisor, float post_scale, void* stream);
 int sa_lookup_backward(const float* grad_out, const float* coords, int64_t coords_bstride, float* const* h_dlevels,
                        const int* h_widths, const int64_t* h_pitches, int num_levels, int radius, int B, int H, int W,
                        int pad0, void* stream);

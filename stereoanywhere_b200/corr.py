@@ -60,21 +60,29 @@ def _no_grad_check(*tensors):
 
 
 class _CorrFn(torch.autograd.Function):
-    """`corr()` with a backward: dL = dV . R / sqrt(C), dR = dV^T . L / sqrt(C) (two batched library GEMMs, fp32)."""
+    """`corr()` with a backward: dL = dV . R / sqrt(C), dR = dV^T . L / sqrt(C).  In "tf32" precision both products
+    run on the tensor cores (`sa_corr_backward_tf32`: the feature maps are K-major operands straight from NCHW);
+    "fp32" (and the C = 3 mono volume) takes two batched fp32 library GEMMs."""
 
     @staticmethod
     def forward(ctx, f2, f3, prec, post_scale):
         ctx.save_for_backward(f2, f3)
         ctx.post_scale = post_scale
+        ctx.prec = prec
         return _OPS.corr_volume(f2, f3, prec, post_scale)
 
     @staticmethod
     def backward(ctx, gvol):
         f2, f3 = ctx.saved_tensors
-        scale = ctx.post_scale / float(torch.sqrt(torch.tensor(f2.shape[1])))
+        need2, need3 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        c, w2, w3 = f2.shape[1], f2.shape[3], f3.shape[3]
+        if ctx.prec == "tf32" and gvol.is_cuda and ops.corr_backward_ok(c, w2, w3):
+            d2, d3 = ops.corr_backward(gvol.float(), f2, f3, ctx.post_scale, need2, need3)
+            return d2, d3, None, None
+        scale = ctx.post_scale / float(torch.sqrt(torch.tensor(c)))
         g = gvol.squeeze(3) * scale                                   # [B,H,W2,W3]
-        d2 = torch.einsum("bhwv,bchv->bchw", g, f3) if ctx.needs_input_grad[0] else None
-        d3 = torch.einsum("bhwv,bchw->bchv", g, f2) if ctx.needs_input_grad[1] else None
+        d2 = torch.einsum("bhwv,bchv->bchw", g, f3) if need2 else None
+        d3 = torch.einsum("bhwv,bchw->bchv", g, f2) if need3 else None
         return d2, d3, None, None
 
 

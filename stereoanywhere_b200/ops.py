@@ -352,6 +352,32 @@ def _volume_entropy_conf(vol: torch.Tensor):
     return _volume_reduce(vol, "entropy_conf")
 
 
+def corr_backward(grad_vol: torch.Tensor, fmap_l: torch.Tensor, fmap_r: torch.Tensor, post_scale: float, need_l: bool,
+                  need_r: bool):
+    """Adjoint of `corr_volume` on the tensor cores (csrc/corr_bwd_tcgen05.cu): grad_vol [B,H,W2,1,W3] ->
+    (grad_l [B,C,H,W2] or None, grad_r [B,C,H,W3] or None).  TF32 operands, fp32 accumulate."""
+    _cuda_f32(grad_vol, "grad_vol")
+    _cuda_f32(fmap_l, "fmap_l")
+    _cuda_f32(fmap_r, "fmap_r")
+    b, c, h, w2 = fmap_l.shape
+    w3 = fmap_r.shape[3]
+    _req(grad_vol.numel() == b * h * w2 * w3, "grad_vol does not match the feature maps")
+    grad_vol, fmap_l, fmap_r = grad_vol.contiguous(), fmap_l.contiguous(), fmap_r.contiguous()
+    gl = torch.empty_like(fmap_l) if need_l else None
+    gr = torch.empty_like(fmap_r) if need_r else None
+    lib = _lib.load()
+    with _on(grad_vol.device):
+        rc = lib.sa_corr_backward_tf32(grad_vol.data_ptr(), fmap_l.data_ptr(), fmap_r.data_ptr(),
+                                       gl.data_ptr() if need_l else None, gr.data_ptr() if need_r else None, b, c, h, w2, w3,
+                                       _divisor(c), float(post_scale), _stream_ptr(grad_vol))
+    _lib.check(rc, "sa_corr_backward_tf32")
+    return gl, gr
+
+
+def corr_backward_ok(c: int, w2: int, w3: int) -> bool:
+    return w2 % 4 == 0 and w3 % 4 == 0 and c >= 8
+
+
 def _lookup_backward(grad_out: torch.Tensor, coords: torch.Tensor, dlevels: List[torch.Tensor], widths: List[int],
                      radius: int, pad0: int) -> None:
     """Accumulate the adjoint of one lookup into the level-gradient buffers `dlevels` (csrc/backward.cu).

@@ -565,9 +565,36 @@ def test_golden_corr_gradients(sa, golden_grads, prec):
         fl, fr = G(g["c_fl"]).requires_grad_(True), G(g["c_fr"]).requires_grad_(True)
         vol = B.corr(fl, fr)
         dfl, dfr = torch.autograd.grad((vol * G(g["c_w"])).sum(), (fl, fr))
-        assert normwise(dfl, g["c_dfl"]) < 2e-6 and normwise(dfr, g["c_dfr"]) < 2e-6  # backward is fp32 GEMM
+        # "fp32": two fp32 library GEMMs; "tf32": sa_corr_backward_tf32 on the tensor cores (north_star: 1e-3 for TF32)
+        tol = 2e-6 if prec == "fp32" else 1e-3
+        assert normwise(dfl, g["c_dfl"]) < tol and normwise(dfr, g["c_dfr"]) < tol
     finally:
         B.precision = old
+
+
+@pytest.mark.parametrize("b,c,h,w2,w3", [(1, 256, 3, 312, 312), (2, 128, 2, 168, 168), (1, 64, 2, 40, 72), (1, 32, 1, 8, 8),
+                                         (1, 256, 1, 768, 768), (1, 160, 2, 240, 236), (1, 96, 2, 132, 264)])
+def test_corr_backward_tensor_core_vs_fp64(sa, b, c, h, w2, w3):
+    """`sa_corr_backward_tf32` (both products of the adjoint of corr(), K-major / MN-major operand paths, K not a
+    multiple of the 32-column stage, channel counts that do not fill the 128-lane tile) against float64."""
+    from stereoanywhere_b200 import ops
+
+    gen = torch.Generator().manual_seed(c + w2 + w3)
+    fl, fr = torch.randn(b, c, h, w2, generator=gen), torch.randn(b, c, h, w3, generator=gen)
+    gv = torch.randn(b, h, w2, 1, w3, generator=gen)
+    dl, dr = ops.corr_backward(gv.to(DEV), fl.to(DEV), fr.to(DEV), 1.0, True, True)
+    g64 = gv.squeeze(3).double() / float(np.float32(np.sqrt(c)))
+    want_l = torch.einsum("bhwv,bchv->bchw", g64, fr.double())
+    want_r = torch.einsum("bhwv,bchw->bchv", g64, fl.double())
+    assert normwise(dl, want_l) < 1e-3 and normwise(dr, want_r) < 1e-3, (normwise(dl, want_l), normwise(dr, want_r))
+    only_l, none_r = ops.corr_backward(gv.to(DEV), fl.to(DEV), fr.to(DEV), 1.0, True, False)
+    assert none_r is None and torch.equal(only_l, dl)
+    # through autograd: corr() in tf32 precision now differentiates on the tensor cores
+    f2, f3 = fl.to(DEV).requires_grad_(True), fr.to(DEV).requires_grad_(True)
+    if c % 32 == 0:
+        vol = sa.CorrBlockB200.corr(f2, f3)
+        a2, a3 = torch.autograd.grad((vol * gv.to(DEV)).sum(), (f2, f3))
+        assert torch.equal(a2, dl) and torch.equal(a3, dr)
 
 
 def test_training_step_gradients_vs_oracle(sa):

@@ -258,6 +258,21 @@ int sa_masked_volume(const float* vol, const float* normals_l, const float* norm
                      float post_scale, const float* mde_l, const float* mde_r, const float* h_edges, int n_bins,
                      float* out, int B, int H, int W2, int W3, void* stream);
 
+/* ---------------------------------------------------------------- producers of the path's inputs
+ *   sa_mono_inputs   mde [B,1,H,W] -> lowres [B,1,Hl,Wl] (Hl = floor(H / 2^n), bilinear, align_corners=True:
+ *                    stereoanywhere.py:109-110), normals [B,3,Hl,Wl] = normalise(-d/dx (g d), -d/dy (g d), 1) with the
+ *                    replicate-padded central difference of kornia's spatial_gradient(mode="diff")
+ *                    (utils/utils.py:73-77; g = normal_gain) and, when masks_f16 != NULL, the one-hot depth bins
+ *                    [B,n_bins,Hl,Wl] as fp16 (utils/utils.py:48-54; h_edges as in sa_masked_volume) - one launch.
+ *   sa_weighted_lsq  scale[b], shift[b] of weighted_lsq (utils/utils.py:345-384) for B samples of n values each
+ *                    (mono / disp / conf: [B, n] fp32): quantile window [min_q, max_q] of relu(disp) by exact radix
+ *                    select (torch.quantile's linear interpolation), weights 0.9 |conf| + 0.1, normal equations in
+ *                    double.  One CTA per sample, no host sync. */
+int sa_mono_inputs(const float* mde, int B, int H, int W, int n_downsample, float normal_gain, const float* h_edges,
+                   int n_bins, float* lowres, float* normals, void* masks_f16, void* stream);
+int sa_weighted_lsq(const float* mono, const float* disp, const float* conf, int B, int n, float min_quantile,
+                    float max_quantile, float* scale, float* shift, void* stream);
+
 /* ---------------------------------------------------------------- A7: training-only corruption
  * mode 0 (roll):  out = vol*(1-m) + roll(vol, shift, dim=W2)*m
  * mode 1 (noise): out = vol*(1-m) + vol*noise[b,h,w2]*m

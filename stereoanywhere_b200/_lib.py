@@ -69,6 +69,10 @@ def _declare(lib):
     lib.sa_lookup_packed_conv.argtypes = [vp, vp, i, vp, i64, vp, vp, vp, vp, i, i, i, vp]
     lib.sa_lookup_factored_conv.restype = i
     lib.sa_lookup_factored_conv.argtypes = [vp, vp, vp, f, f, i, vp, i64, vp, vp, vp, vp, i, i, i, vp]
+    lib.sa_mono_inputs.restype = i
+    lib.sa_mono_inputs.argtypes = [vp, i, i, i, i, f, C.POINTER(f), i, vp, vp, vp, vp]
+    lib.sa_weighted_lsq.restype = i
+    lib.sa_weighted_lsq.argtypes = [vp, vp, vp, i, i, f, f, vp, vp, vp]
     lib.sa_truncate.restype = i
     lib.sa_truncate.argtypes = [vp, vp, vp, d, vp, i64, i, i, vp]
     lib.sa_masked_volume.restype = i
@@ -79,7 +83,7 @@ def _declare(lib):
 
 EXPORTS = [
     "sa_abi_version", "sa_last_error", "sa_corr_fp32", "sa_corr_tf32", "sa_pyramid", "sa_lookup", "sa_lookup2",
-    "sa_truncate", "sa_masked_volume", "sa_corrupt", "sa_packed_row_floats", "sa_pack_pyramid", "sa_pack_pyramid_normals", "sa_lookup_packed", "sa_lookup_packed_conv", "sa_lookup_factored_conv", "sa_corr_pack_tf32", "sa_stitch_tile", "sa_stitch_finish", "sa_lookup_packed_normals", "sa_lookup_packed_factored", "sa_corr_backward_tf32", "sa_lookup_backward", "sa_pyramid_backward", "sa_volume_softargmax", "sa_volume_entropy_conf",
+    "sa_truncate", "sa_masked_volume", "sa_corrupt", "sa_packed_row_floats", "sa_pack_pyramid", "sa_pack_pyramid_normals", "sa_lookup_packed", "sa_lookup_packed_conv", "sa_lookup_factored_conv", "sa_corr_pack_tf32", "sa_mono_inputs", "sa_weighted_lsq", "sa_stitch_tile", "sa_stitch_finish", "sa_lookup_packed_normals", "sa_lookup_packed_factored", "sa_corr_backward_tf32", "sa_lookup_backward", "sa_pyramid_backward", "sa_volume_softargmax", "sa_volume_entropy_conf",
 ]
 
 

@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 OBJDIR = os.path.join(PKG, "build")
 LIB = os.path.join(LIBDIR, "libsa_b200.so")
-SOURCES = ["capi.cu", "lookup.cu", "pyramid.cu", "corr_simt.cu", "corr_tcgen05.cu", "corr_pack_tcgen05.cu", "volume_ops.cu", "packed.cu", "lookup_conv.cu", "volume_reduce.cu", "backward.cu", "volume_rows.cu", "stitch.cu", "corr_bwd_tcgen05.cu"]
+SOURCES = ["capi.cu", "lookup.cu", "pyramid.cu", "corr_simt.cu", "corr_tcgen05.cu", "corr_pack_tcgen05.cu", "volume_ops.cu", "packed.cu", "lookup_conv.cu", "volume_reduce.cu", "backward.cu", "volume_rows.cu", "stitch.cu", "corr_bwd_tcgen05.cu", "producers.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -1,5 +1,10 @@
 """Producer chain of the path's inputs, without host syncs or per-sample Python loops.
 
+Two forms.  `mono_inputs` and `weighted_lsq_b200` are the CUDA kernels (csrc/producers.cu, CUDA tensors only):
+resize + normals + depth bins in one launch, and the per-sample scale / shift fit in one launch for the whole
+batch (exact radix-select quantiles, normal equations in double).  The functions below them are the same
+arithmetic as device-agnostic batched tensor ops (the host mirror the CPU tests pin against the reference).
+
 The reference forms the inputs of the mono volume and of the truncation mask with a handful of small ops on
 `[B,1,H/4,W/4]` maps (stereoanywhere.py:109-114, 138-139, 191): a bilinear 1/4 resize, `estimate_normals`
 (utils/utils.py:73-77), `generate_masks` (:48-54) and the per-sample `weighted_lsq` (:345-384), whose Python loop
@@ -16,10 +21,59 @@ oracle/ref_shim.py (replicate pad, central difference without the 1/2 factor).
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.nn.functional as F
+
+
+def mono_inputs(mde: torch.Tensor, n_downsample: int = 2, normal_gain: Optional[float] = None, n_bins: int = 8,
+                with_masks: bool = True):
+    """`(mde_lowres [B,1,H/4,W/4], normals [B,3,H/4,W/4], masks [B,N,H/4,W/4] fp16 or None)` of a full-resolution mono
+    depth `[B,1,H,W]` in ONE kernel (`sa_mono_inputs`): the resize of stereoanywhere.py:109-110, `estimate_normals`
+    (:113-114; `normal_gain` defaults to the model's `W_lowres / 10`, :46,113) and `generate_masks` (:138-139)."""
+    from . import _lib, ops
+
+    ops._cuda_f32(mde, "mde")
+    ops._req(mde.dim() == 4 and mde.shape[1] == 1, "mde must be [B,1,H,W]")
+    b, _, h, w = mde.shape
+    mde = mde.contiguous()
+    hl, wl = int(h * (1.0 / 2 ** n_downsample)), int(w * (1.0 / 2 ** n_downsample))
+    if normal_gain is None:
+        normal_gain = (w // (2 ** n_downsample)) / 10
+    low = torch.empty((b, 1, hl, wl), dtype=torch.float32, device=mde.device)
+    normals = torch.empty((b, 3, hl, wl), dtype=torch.float32, device=mde.device)
+    masks = torch.empty((b, n_bins, hl, wl), dtype=torch.float16, device=mde.device) if with_masks else None
+    lib = _lib.load()
+    with ops._on(mde.device):
+        rc = lib.sa_mono_inputs(mde.data_ptr(), b, h, w, n_downsample, float(normal_gain), ops.bin_edges(n_bins), n_bins,
+                                low.data_ptr(), normals.data_ptr(), masks.data_ptr() if with_masks else None,
+                                ops._stream_ptr(mde))
+    _lib.check(rc, "sa_mono_inputs")
+    return low, normals, masks
+
+
+def weighted_lsq_b200(mde: torch.Tensor, disp: torch.Tensor, conf: torch.Tensor, min_quantile: float = 0.2,
+                      max_quantile: float = 0.9) -> Tuple[torch.Tensor, torch.Tensor]:
+    """`weighted_lsq` (utils/utils.py:345-384) for the whole batch in ONE launch, no host sync (`sa_weighted_lsq`).
+    Same call shape as the reference: `[B,C,H,W]` maps (the model passes left and right stacked on C,
+    stereoanywhere.py:191), returns `(scale, shift)` as `[B,1,1,1]`."""
+    from . import _lib, ops
+
+    b = mde.shape[0]
+    dt = mde.dtype
+    mono, st, cf = (t.reshape(b, -1).float().contiguous() for t in (mde, disp, conf))
+    for t, n in ((mono, "mde"), (st, "disp"), (cf, "conf")):
+        ops._cuda_f32(t, n)
+    ops._req(mono.shape == st.shape == cf.shape, "mde / disp / conf must have the same number of elements per sample")
+    scale = torch.empty(b, dtype=torch.float32, device=mono.device)
+    shift = torch.empty_like(scale)
+    lib = _lib.load()
+    with ops._on(mono.device):
+        rc = lib.sa_weighted_lsq(mono.data_ptr(), st.data_ptr(), cf.data_ptr(), b, mono.shape[1], float(min_quantile),
+                                 float(max_quantile), scale.data_ptr(), shift.data_ptr(), ops._stream_ptr(mono))
+    _lib.check(rc, "sa_weighted_lsq")
+    return scale.reshape(b, 1, 1, 1).to(dt), shift.reshape(b, 1, 1, 1).to(dt)
 
 
 def generate_masks(mde: torch.Tensor, N: int = 16) -> torch.Tensor:

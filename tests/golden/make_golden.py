@@ -17,6 +17,8 @@ tests need (the lookups of model_slice were produced from the very volumes store
                      `StereoAnywhere({}).forward(..., iters=6, test_mode=True)` on a 64x128 pair:
                      inputs of both `corr()` calls, the tensors handed to both block
                      constructors, and (coords, stereo lookup, mono lookup) per GRU iteration.
+* producers_chain.npz - SURVEY 8f-3 as the model chains it: full-resolution mono depth -> 1/4 resize -> normals -> depth
+                     bins, and weighted_lsq at a model-like size (fixtures of the CUDA producer kernels).
 * tiles.npz        - tile enumeration for several (H, W, preset) pairs, blend weights, pad
                      geometry and a stitched output of the real `TileWrapper` around a toy model.
 """
@@ -323,9 +325,42 @@ def producers():
     print("producers.npz", sum(np.asarray(v).nbytes for v in out.values()) / 1e6, "MB raw")
 
 
+def producers_chain():
+    """SURVEY 8f-3, the chain as the model runs it (stereoanywhere.py:109-114, 138-139): full-resolution mono depth ->
+    1/4 bilinear resize (align_corners) -> estimate_normals (kornia stub) -> generate_masks; and weighted_lsq at a
+    model-like size with a quantile window that cuts through ties (relu zeros)."""
+    import torch.nn.functional as F
+
+    _, U = ref_shim.import_reference_corr()
+    g = torch.Generator().manual_seed(2468)
+    out = {}
+    for tag, (b, h, w) in {"a": (2, 64, 96), "b": (1, 36, 52)}.items():
+        yy = torch.linspace(0, 1, h).view(1, 1, h, 1)
+        xx = torch.linspace(0, 1, w).view(1, 1, 1, w)
+        mde = (0.3 + 0.5 * xx + 0.1 * torch.sin(7 * yy + 3 * xx) + 0.05 * torch.rand(b, 1, h, w, generator=g)).clamp(0, 1)
+        mde[0, 0, 0, 0] = 1.0
+        low = F.interpolate(mde, scale_factor=1 / 4, mode="bilinear", align_corners=True)
+        w_low = w // 4
+        normals = U.estimate_normals(low, normal_gain=(w_low / 10))
+        out[f"{tag}_mde"] = _np(mde)
+        out[f"{tag}_low"] = _np(low)
+        out[f"{tag}_normals"] = _np(normals)
+        out[f"{tag}_masks8"] = _np(U.generate_masks(low, N=8))
+        out[f"{tag}_gain"] = np.array([w_low / 10], dtype=np.float64)
+    b, h, w = 4, 48, 64
+    mono = torch.rand(b, 2, h, w, generator=g)
+    disp = (mono * torch.tensor([30.0, 12.0, 5.0, 1.5]).view(b, 1, 1, 1) - torch.tensor([10.0, 2.0, 0.0, -1.0]).view(b, 1, 1, 1)
+            + 0.3 * torch.randn(b, 2, h, w, generator=g))      # a third of the first sample is negative -> relu zeros
+    conf = torch.rand(b, 2, h, w, generator=g) * 0.01
+    sc, sh = U.weighted_lsq(mono, disp, conf)
+    out.update(wl_mono=_np(mono), wl_disp=_np(disp), wl_conf=_np(conf), wl_scale=_np(sc), wl_shift=_np(sh))
+    np.savez_compressed(os.path.join(HERE, "producers_chain.npz"), **out)
+    print("producers_chain.npz", sum(np.asarray(v).nbytes for v in out.values()) / 1e6, "MB raw")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     table = {"path_small": path_small, "model_slice": model_slice, "tiles": tiles, "reductions": reductions, "grads": grads,
-             "producers": producers}
+             "producers": producers, "producers_chain": producers_chain}
     for name in sys.argv[1:] or list(table):
         table[name]()

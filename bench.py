@@ -487,7 +487,9 @@ def run_gpu(args):
     d2h = res_s.numel() * 4 * 2
     paths = [GpuPath(sa, sset, args.variant, args.mono) for sset in sets]
     copy_stream = torch.cuda.Stream()
+    d2h_stream = torch.cuda.Stream()                 # results leave on their own stream: H2D / compute / D2H overlap
     main_stream = torch.cuda.current_stream()
+    computed = [torch.cuda.Event() for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]   # upload of set i finished
     freed = [torch.cuda.Event() for _ in range(2)]   # compute on set i finished (buffers reusable)
 
@@ -509,8 +511,14 @@ def run_gpu(args):
             main_stream.wait_event(ready[i])
             s, mm, _ = paths[i].step()
             freed[i].record(main_stream)
-            res_s.copy_(s, non_blocking=True)
-            res_m.copy_(mm, non_blocking=True)
+            computed[i].record(main_stream)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(computed[i])
+                res_s.copy_(s, non_blocking=True)
+                res_m.copy_(mm, non_blocking=True)
+                s.record_stream(d2h_stream)
+                mm.record_stream(d2h_stream)
+        main_stream.wait_stream(d2h_stream)          # the closing event covers the last read-back
 
     e2e_run(3)
     barrier()

@@ -10,6 +10,8 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libsa_b200.so")
+#: development only: load another build of the library (kernel experiments; see tools/build_variant.sh)
+_LIB_OVERRIDE = os.environ.get("SA_B200_LIB")
 
 _lib = None
 
@@ -111,7 +113,7 @@ def load():
                 f"stereoanywhere_b200: {LIB_PATH} was built from different sources than csrc/ and the rebuild "
                 f"failed ({e}); fix the build or run `python -m stereoanywhere_b200.build --force`") from e
     try:
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(_LIB_OVERRIDE or LIB_PATH)
         _declare(lib)
     except (OSError, AttributeError) as stale:
         raise SaError(f"stereoanywhere_b200: {LIB_PATH} does not match this binding ({stale}); "

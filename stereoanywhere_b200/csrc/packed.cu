@@ -17,8 +17,10 @@
 // any tap of any level is inside the image.  One lookup = one line per (pixel, volume): 128 B read
 // + 144 B written, below the 308 B/px "algorithmic" figure of the unpacked formulation.
 #include <stdlib.h>
+#include <string.h>
 
 #include "sa_common.cuh"
+#include "tc_common.cuh"
 
 namespace sa {
 
@@ -308,58 +310,86 @@ __device__ __forceinline__ void blend_windows(float (&l0)[17], float (&l1)[13], 
 // two FFMA per entry) and store the chunk; everything after staging is the packed path unchanged.  Differences
 // from the packed mono volume are fp32 rounding only (the scale is applied to the coefficients, and the 15 stored
 // border entries of levels 1..3 are pooled before the contraction instead of after it): <= 4e-7 for unit normals.
-template <int NV, int TILE, int OTF, int FV>
-__global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupArgs a) {
+// zero-filling form of cp.async: `bytes` = 16 copies the chunk, 0 writes sixteen zero bytes without reading (a pixel
+// whose window lies wholly outside the row) - no branch in the staging loop
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, unsigned bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc),
+               "r"(bytes)
+               : "memory");
+}
+
+// All global addressing below is `uniform 64-bit base + 32-bit unsigned index` in units of 16 bytes (one chunk of a
+// line, one float4 of the output): a packed array of up to 64 GB.  The first version formed every address in 64 bits
+// per thread - 370 of its 950 SASS instructions were integer address arithmetic in a kernel that is issue-bound
+// (DESIGN 7c); see profiles/r2 for the before / after instruction mix.
+// 48 registers: 21 CTAs of 64 threads per SM instead of 18 (the compiler would take 55; the factored form spills one
+// value) - the kernel is latency-bound, resident warps are what hides its three dependent phases.
+#ifndef SA_LOOKUP_REGS_TMA
+#define SA_LOOKUP_REGS_TMA 56
+#endif
+#ifndef SA_LOOKUP_REGS_VEC
+#define SA_LOOKUP_REGS_VEC 48
+#endif
+template <int NV, int TILE, int OTF, int FV, bool TMA>
+__global__ void __maxnreg__(TMA ? SA_LOOKUP_REGS_TMA : SA_LOOKUP_REGS_VEC) lookup_packed_kernel(const PLookupArgs a, const __grid_constant__ CUtensorMap map_o0,
+                                                     const __grid_constant__ CUtensorMap map_o1) {
   static_assert(OTF < 0 || FV < 0, "one special mono form at a time");
   constexpr int THREADS = NV * TILE;
   constexpr int NC = 36;
-  constexpr int SP = TILE + 4;
+  // TMA: dense [channel][pixel] tile, stored by the TMA unit; else padded rows for the transposed 128-bit re-read
+  constexpr int SP = TMA ? TILE : TILE + 4;
   constexpr int STAGE_FLOATS = NV * TILE * 32;
   constexpr int OUT_FLOATS = NV * NC * SP;
   constexpr int BUF_FLOATS = STAGE_FLOATS > OUT_FLOATS ? STAGE_FLOATS : OUT_FLOATS;
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float* buf = smem;                                        // staging lines, later the output tile
   float* s_x = smem + BUF_FLOATS;                           // [TILE] x coordinate
-  int* s_blk = reinterpret_cast<int*>(s_x + TILE);          // [TILE] block index or -1
-  // FV >= 0: per pixel {k n0, k n1, k n2, float offset of line (h, blk) inside a channel of the batch's rows}
+  unsigned* s_line = reinterpret_cast<unsigned*>(s_x + TILE);  // [TILE] index of the pixel's line in 16-byte chunks, or ~0u
+  // FV >= 0: per pixel {k n0, k n1, k n2, chunk index of line (c = 0, h, blk) of the packed right normals}
   float4* s_n = reinterpret_cast<float4*>(s_x + 2 * TILE);
 
   const int tid = threadIdx.x;
-  const int b = blockIdx.y;
-  const int hw0 = blockIdx.x * TILE;
-  const int npx = min(TILE, a.HW - hw0);
-  const long long row0 = (long long)b * a.HW + hw0;
+  const unsigned b = blockIdx.y;
+  const unsigned hw0 = blockIdx.x * TILE;
+  const int npx = min(TILE, a.HW - (int)hw0);
 
   if (tid < TILE) {
     float x = 0.f;
-    int blk = -1;
+    unsigned line = ~0u;
     float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+    int blk = -1;
     if (tid < npx) {
-      x = __ldg(a.coords + (long long)b * a.coords_bstride + hw0 + tid);
+      x = __ldg(a.coords + (size_t)b * a.coords_bstride + hw0 + tid);
       if (FV >= 0) {  // issued together with the coordinate load: they do not depend on it
-        const long long plane = (long long)a.H * a.Wimg;
-        const float* nlp = a.nl + (long long)b * 3 * plane + hw0 + tid;  // h * Wimg + w2 == hw
+        const unsigned plane = (unsigned)a.H * a.Wimg;
+        const float* nlp = a.nl + (size_t)(b * 3 * plane + hw0 + tid);  // h * Wimg + w2 == hw
         n0 = __ldg(nlp); n1 = __ldg(nlp + plane); n2 = __ldg(nlp + 2 * plane);
       }
       const float fl = fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
       const int q = ((int)fl >> 3) - kQMin;
-      if (q >= 0 && q < a.nblk) blk = q;
+      if (q >= 0 && q < a.nblk) {
+        blk = q;
+        line = ((b * (unsigned)a.HW + hw0 + tid) * (unsigned)a.nblk + (unsigned)q) * 8u;
+      }
     }
     s_x[tid] = x;
-    s_blk[tid] = blk;
+    s_line[tid] = line;
     if (FV >= 0) {
-      // a pixel without a line (blk < 0) reads line 0 with zero coefficients: no branch in the staging loop
+      // a pixel without a line (blk < 0) reads line 0 with zero coefficients: no branch in the staging loop.
+      // Image row of the pixel: the CTA's first pixel is in row h0 (uniform division), a pixel of the tile at most
+      // four rows further down (TILE <= 32 + ... and Wimg >= 8) - no per-thread division.
       const float k = blk >= 0 ? a.post_scale * a.inv_divisor : 0.f;
-      const int off = blk >= 0 ? (((hw0 + tid) / a.Wimg) * a.nblk + blk) * 32 : 0;
-      s_n[tid] = make_float4(n0 * k, n1 * k, n2 * k, __int_as_float(off));
+      const unsigned h0 = hw0 / (unsigned)a.Wimg;
+      const unsigned t = hw0 - h0 * (unsigned)a.Wimg + tid;
+      unsigned hh = h0;
+      for (unsigned w = a.Wimg; w <= t; w += a.Wimg) ++hh;
+      const unsigned off = blk >= 0 ? (((b * 3u) * a.H + hh) * (unsigned)a.nblk + (unsigned)blk) * 8u : 0u;
+      s_n[tid] = make_float4(n0 * k, n1 * k, n2 * k, __uint_as_float(off));
     }
   }
   else if (NV == 2 && a.pf_dist > 0) {
-    // The second half of the CTA has nothing to do in the prologue.  It reads the coordinates of the CTA that
-    // will run `pf_dist` CTAs later and issues an L2 prefetch of that CTA's packed lines: by the time that CTA
-    // stages them they come out of L2 instead of HBM, and the HBM requests of a launch are spread over its whole
-    // duration instead of being issued only by the ~15 % of resident CTAs that are in their staging phase
-    // (the kernel is latency-bound: DRAM ~30 % busy).  No registers held, no dependence on the result.
+    // Optional (SA_B200_LOOKUP_PF, off by default: measured neutral, profiles/r2/lookup_l2_prefetch_sweep.txt): the
+    // second half of the CTA, idle in the prologue, pulls the lines of the CTA `pf_dist` launches ahead into L2.
     const int t = tid - TILE;
     const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + a.pf_dist;
     if (lin < (long long)gridDim.x * gridDim.y) {
@@ -382,46 +412,42 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
 
   // ---- stage one line per (pixel, volume): 8 lanes x 16 B, chunk c of pixel p lands at chunk c ^ (p & 7).
   // Thread tid copies chunk ch = tid & 7 of the units (tid >> 3) + n * THREADS/8, n < 8: the volume of a unit is
-  // a compile-time function of n and its pixel one of 8/NV values, so the 64-bit line addresses are formed
-  // 8/NV times per thread and shared by the volumes.  (Forming them once per pixel in the prologue and passing
-  // them through shared memory saves 30 instructions per thread and changes nothing: 23.25 us - latency-bound.)
+  // a compile-time function of n and its pixel one of 8/NV values, so a line index is read 8/NV times per thread
+  // and shared by the volumes.
   {
     constexpr int UPS = THREADS / 8;   // units per step
     constexpr int SPV = 8 / NV;        // steps per volume
-    const int ch = tid & 7, u0 = tid >> 3;
-    long long goff[SPV];               // float offset of this thread's chunk inside a packed array, or -1
+    const unsigned ch = tid & 7, u0 = tid >> 3;
+    const float4* p0 = reinterpret_cast<const float4*>(a.packed[0]);
+    const float4* p1 = reinterpret_cast<const float4*>(NV == 2 ? a.packed[1] : a.packed[0]);
 #pragma unroll
     for (int m = 0; m < SPV; ++m) {
-      const int pm = u0 + m * UPS;
-      const int blk = s_blk[pm];
-      goff[m] = blk >= 0 ? ((row0 + pm) * (long long)a.nblk + blk) * 32 + ch * 4 : -1;
-    }
+      const unsigned pm = u0 + m * UPS;
+      const unsigned line = s_line[pm];
+      const unsigned ok = line != ~0u ? 16u : 0u;
+      const unsigned idx = (line != ~0u ? line : 0u) + ch;
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const int v = n / SPV, m = n % SPV;  // compile-time
-      if (v == OTF || v == FV) continue;
-      const int pm = u0 + m * UPS;
-      float* dst = buf + (v * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2);
-      if (goff[m] >= 0)
-        cp_async16(dst, (v ? a.packed[1] : a.packed[0]) + goff[m]);
-      else
-        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int v = 0; v < NV; ++v) {
+        if (v == OTF || v == FV) continue;
+        float* dst = buf + (v * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2);
+        cp_async16_zfill(dst, (v ? p1 : p0) + idx, ok);
+      }
     }
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   if (FV >= 0) {
     // the factored volume's chunks while the copies above are in flight: all loads first, then the arithmetic
     constexpr int UPS = THREADS / 8, SPV = 8 / NV;
-    const int ch = tid & 7, u0 = tid >> 3;
-    const int cplane = a.H * a.nblk * 32;  // floats between the channels of one (b, h)
-    const float* rp = a.packed[FV >= 0 ? FV : 0] + (long long)b * 3 * cplane + ch * 4;
+    const unsigned ch = tid & 7, u0 = tid >> 3;
+    const unsigned cplane = (unsigned)a.H * a.nblk * 8u;  // chunks between the channels of one (b, h)
+    const float4* rp = reinterpret_cast<const float4*>(a.packed[FV >= 0 ? FV : 0]);
     float4 r[SPV][3], n[SPV];
 #pragma unroll
     for (int m = 0; m < SPV; ++m) {
       n[m] = s_n[u0 + m * UPS];
-      const int off = __float_as_int(n[m].w);
+      const unsigned off = __float_as_uint(n[m].w) + ch;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) r[m][c] = __ldg(reinterpret_cast<const float4*>(rp + (off + c * cplane)));
+      for (int c = 0; c < 3; ++c) r[m][c] = __ldg(rp + (off + c * cplane));
     }
 #pragma unroll
     for (int m = 0; m < SPV; ++m) {
@@ -449,10 +475,11 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
     for (int i = 0; i < 11; ++i) l2[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < 10; ++i) l3[i] = 0.f;
-    const int blk = s_blk[p];
-    if (blk >= 0) {
+    const unsigned line_p = s_line[p];
+    if (line_p != ~0u) {
+      const int blk = (int)((line_p >> 3) % (unsigned)a.nblk);
       const int c0 = 8 * (blk + kQMin) - 32;
-      const int hw = hw0 + p;
+      const int hw = (int)hw0 + p;
       const int hh = hw / a.Wimg, w2 = hw - hh * a.Wimg;
       const long long plane2 = (long long)a.H * a.Wimg, plane3 = (long long)a.H * a.W3;
       const float* nlp = a.nl + ((long long)b * 3 * a.H + hh) * a.Wimg + w2;
@@ -509,25 +536,40 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
   __syncthreads();  // staging is dead: `buf` becomes the [channel][pixel] output tile
 
   blend_windows(l0, l1, l2, l3, s_x[p], [&](int c, float val) { buf[(v * NC + c) * SP + p] = val; });
-  __syncthreads();
 
-  // ---- [channel][pixel] tile -> NCHW
+  // ---- [channel][pixel] tile -> NCHW.  One TMA tensor store per volume (box {TILE pixels, 36 channels, 1} of the
+  // map {HW, 36, B}; pixels beyond HW are clipped by the map) instead of 9 LDS.128 + 9 STG.128 per thread: the
+  // kernel is bound by L1 / shared-memory wavefronts (ncu: l1tex 59 % busy, 31 % of the stall samples on the
+  // shared-memory scoreboard / MIO queue), and those 18 instructions were 27 % of its wavefronts.
+  if (TMA) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid < NV) {
+      tma_store_3d(tid ? &map_o1 : &map_o0, buf + tid * NC * SP, (int)hw0, 0, (int)b);
+      tma_commit();
+      tma_wait_read<0>();   // the tile must outlive the store's read of it
+    }
+    return;
+  }
+  __syncthreads();
   if ((a.HW & 3) == 0) {
-    // thread tid always stores pixels t .. t+3 of the channels c0 + 4 NV k, k < NC/4: one pointer per volume,
-    // advanced by a constant stride - no division, no 64-bit multiply in the loop
+    // thread tid always stores pixels t .. t+3 of the channels c0 + 4 NV k, k < NC/4: one 32-bit float4 index per
+    // volume, advanced by a constant stride
     constexpr int T4 = TILE / 4;
     static_assert(THREADS == 4 * NV * T4 && NC % 4 == 0, "store mapping");
     const int c0 = tid / T4, t = (tid % T4) * 4;
     if (t < npx) {
-      const long long pix = (long long)b * NC * a.HW + hw0 + t;
-      const long long cstride = (long long)a.HW;
+      const unsigned hw4 = (unsigned)a.HW >> 2;
+      float4* o0 = reinterpret_cast<float4*>(a.out[0]);
+      float4* o1 = reinterpret_cast<float4*>(NV == 2 ? a.out[1] : a.out[0]);
+      const unsigned pix4 = b * NC * hw4 + ((hw0 + t) >> 2);
 #pragma unroll
       for (int k = 0; k < NC / 4; ++k) {
         const int c = c0 + 4 * NV * k;          // 0 .. NV*NC-1
         const int vv = (NV == 2 && c >= NC) ? 1 : 0;
         const int cc = c - vv * NC;
         const float4 val = *reinterpret_cast<const float4*>(buf + c * SP + t);
-        st_stream_v4((vv ? a.out[1] : a.out[0]) + pix + cc * cstride, val);
+        st_stream_v4(reinterpret_cast<float*>((vv ? o1 : o0) + (pix4 + cc * hw4)), val);
       }
     }
   } else {
@@ -541,19 +583,68 @@ __global__ void __launch_bounds__(NV * TILE) lookup_packed_kernel(const PLookupA
   }
 }
 
-template <int NV, int TILE, int OTF, int FV>
-static int launch_packed_t(const PLookupArgs& a, int B, cudaStream_t st) {
-  constexpr int NC = 36, SP = TILE + 4;
+// Output tensor map {HW, 36, B} with box {TILE, 36, 1}; encoding one costs ~1 us of host time, so the last few
+// (pointer, geometry) combinations are kept per thread - torch's caching allocator hands the same blocks back.
+static int output_map(CUtensorMap* m, const float* out, int B, int HW, int tile) {
+  struct Entry { const float* p; int B, HW, tile; CUtensorMap m; };
+  static thread_local Entry cache[16];
+  static thread_local int next = 0;
+  for (int i = 0; i < 16; ++i)
+    if (cache[i].p == out && cache[i].B == B && cache[i].HW == HW && cache[i].tile == tile) {
+      *m = cache[i].m;
+      return 0;
+    }
+  EncodeTiledFn fn = encode_fn();
+  SA_REQUIRE(fn != nullptr, SA_E_UNSUPPORTED, "cuTensorMapEncodeTiled unavailable (no driver?)");
+  cuuint64_t dims[3] = {(cuuint64_t)HW, 36, (cuuint64_t)B};
+  cuuint64_t str[2] = {(cuuint64_t)HW * 4, (cuuint64_t)HW * 36 * 4};
+  cuuint32_t box[3] = {(cuuint32_t)tile, 36, 1};
+  cuuint32_t ones[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(out), dims, str, box, ones,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SA_REQUIRE(r == CUDA_SUCCESS, SA_E_INVALID, "cuTensorMapEncodeTiled(lookup output) failed with CUresult %d", (int)r);
+  cache[next] = Entry{out, B, HW, tile, *m};
+  next = (next + 1) & 15;
+  return 0;
+}
+
+template <int NV, int TILE, int OTF, int FV, bool TMA>
+static int launch_packed_tt(PLookupArgs a, int B, cudaStream_t st) {
+  constexpr int NC = 36, SP = TMA ? TILE : TILE + 4;
   constexpr int buf_floats = (NV * TILE * 32 > NV * NC * SP) ? NV * TILE * 32 : NV * NC * SP;
-  const size_t smem = (size_t)(buf_floats + (FV >= 0 ? 6 : 2) * TILE) * sizeof(float)  /* s_x, s_blk [, float4 s_n] */;
-  auto kern = lookup_packed_kernel<NV, TILE, OTF, FV>;
+  const size_t smem = (size_t)(buf_floats + (FV >= 0 ? 6 : 2) * TILE) * sizeof(float)  /* s_x, s_line [, float4 s_n] */;
+  auto kern = lookup_packed_kernel<NV, TILE, OTF, FV, TMA>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) SA_FAIL((int)e, "sa_lookup_packed: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
+  CUtensorMap m0, m1;
+  memset(&m0, 0, sizeof(m0));
+  memset(&m1, 0, sizeof(m1));
+  if (TMA) {
+    int rc = output_map(&m0, a.out[0], B, a.HW, TILE);
+    if (rc) return rc;
+    if (NV == 2) {
+      rc = output_map(&m1, a.out[1], B, a.HW, TILE);
+      if (rc) return rc;
+    }
+  }
   dim3 grid((a.HW + TILE - 1) / TILE, B);
-  kern<<<grid, NV * TILE, smem, st>>>(a);
+  kern<<<grid, NV * TILE, smem, st>>>(a, m0, m1);
   return finish_launch("sa_lookup_packed");
+}
+
+// Output path.  Factored mono form: one TMA tensor store per volume (22.9 us per dual lookup at KITTI size against
+// 23.8 with the transposed 128-bit stores - it is bound by L1 / shared-memory wavefronts).  Two packed volumes: the
+// 128-bit stores (23.2 against 24.4 us with TMA stores - that form is DRAM-bound and its streaming `no_allocate`
+// stores disturb the line reads less).  SA_B200_LOOKUP_TMA=0/1 overrides.
+template <int NV, int TILE, int OTF, int FV>
+static int launch_packed_t(const PLookupArgs& a, int B, cudaStream_t st) {
+  static const int env = getenv("SA_B200_LOOKUP_TMA") ? atoi(getenv("SA_B200_LOOKUP_TMA")) : -1;
+  const bool want = env >= 0 ? env != 0 : (FV >= 0);
+  if (want && (a.HW & 3) == 0 && encode_fn() != nullptr) return launch_packed_tt<NV, TILE, OTF, FV, true>(a, B, st);
+  return launch_packed_tt<NV, TILE, OTF, FV, false>(a, B, st);
 }
 
 template <int NV, int OTF, int FV = -1>
@@ -632,6 +723,8 @@ extern "C" int sa_lookup_packed(const float* packed_a, const float* packed_b, in
   SA_REQUIRE((packed_b == nullptr) == (out_b == nullptr), SA_E_INVALID, "sa_lookup_packed: packed_b / out_b must come together");
   SA_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 31), SA_E_INVALID, "sa_lookup_packed: bad sizes");
   SA_REQUIRE(W3 >= 8 && W3 % 8 == 0, SA_E_UNSUPPORTED, "sa_lookup_packed: W3 must be a multiple of 8");
+  SA_REQUIRE((long long)B * H * W * packed_blocks(W3) < (1ll << 29), SA_E_UNSUPPORTED,
+             "sa_lookup_packed: packed array of 64 GB or more (32-bit chunk indices)");
   SA_REQUIRE(aligned16(packed_a) && aligned16(out_a) && (!packed_b || (aligned16(packed_b) && aligned16(out_b))), SA_E_ALIGN,
              "sa_lookup_packed: pointers must be 16-byte aligned");
   (void)num_sms();
@@ -652,6 +745,8 @@ extern "C" int sa_lookup_packed_normals(const float* packed_a, const float* norm
   SA_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 31) && divisor != 0.f, SA_E_INVALID,
              "sa_lookup_packed_normals: bad sizes");
   SA_REQUIRE(W3 >= 8 && W3 % 8 == 0, SA_E_UNSUPPORTED, "sa_lookup_packed_normals: W3 must be a multiple of 8");
+  SA_REQUIRE((long long)B * H * W * packed_blocks(W3) < (1ll << 29), SA_E_UNSUPPORTED,
+             "sa_lookup_packed_normals: packed array of 64 GB or more (32-bit chunk indices)");
   SA_REQUIRE(aligned16(normals_r) && aligned16(out_mono) && (!packed_a || (aligned16(packed_a) && aligned16(out_a))), SA_E_ALIGN,
              "sa_lookup_packed_normals: pointers must be 16-byte aligned");
   (void)num_sms();
@@ -678,6 +773,8 @@ extern "C" int sa_lookup_packed_factored(const float* packed_a, const float* pac
   SA_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 31) && divisor != 0.f, SA_E_INVALID,
              "sa_lookup_packed_factored: bad sizes");
   SA_REQUIRE(W3 >= 8 && W3 % 8 == 0, SA_E_UNSUPPORTED, "sa_lookup_packed_factored: W3 must be a multiple of 8");
+  SA_REQUIRE((long long)B * H * W * packed_blocks(W3) < (1ll << 29), SA_E_UNSUPPORTED,
+             "sa_lookup_packed_factored: packed array of 64 GB or more (32-bit chunk indices)");
   SA_REQUIRE(aligned16(packed_normals_r) && aligned16(out_mono) && (!packed_a || (aligned16(packed_a) && aligned16(out_a))),
              SA_E_ALIGN, "sa_lookup_packed_factored: pointers must be 16-byte aligned");
   (void)num_sms();

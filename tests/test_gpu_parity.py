@@ -325,14 +325,38 @@ def test_edge_cases(sa):
 
 # ------------------------------------------------------------------------------------------ full size, properties
 
-@pytest.mark.parametrize("cfg", ["c1", "c2"])
+def sampled_closed_lookup(vol_rows, xs, num_levels=4, radius=4):
+    """float64 closed form of the lookup for sampled volume rows `[n, W]` at coordinates `xs [n]`:
+    `[n, num_levels * (2 radius + 1)]`."""
+    lv = vol_rows.double()
+    xs = xs.double()
+    outs = []
+    for i in range(num_levels):
+        w_i = lv.shape[1]
+        padded = torch.nn.functional.pad(lv, (radius + 2, radius + 2))      # zeros outside the row
+        x = xs / (2 ** i)
+        x0 = torch.floor(x)
+        f = (x - x0).unsqueeze(1)
+        k = torch.arange(-radius, radius + 1, device=lv.device, dtype=torch.float64).unsqueeze(0)
+        j = (x0.unsqueeze(1) + k).clamp(-radius - 2, w_i + radius).long() + radius + 2
+        a = torch.gather(padded, 1, j.clamp(0, padded.shape[1] - 1))
+        b_ = torch.gather(padded, 1, (j + 1).clamp(0, padded.shape[1] - 1))
+        inside_a = ((x0.unsqueeze(1) + k) >= 0) & ((x0.unsqueeze(1) + k) < w_i)
+        inside_b = ((x0.unsqueeze(1) + k + 1) >= 0) & ((x0.unsqueeze(1) + k + 1) < w_i)
+        outs.append((1 - f) * a * inside_a + f * b_ * inside_b)
+        lv = 0.5 * (lv[:, 0:2 * (w_i // 2):2] + lv[:, 1:2 * (w_i // 2):2])
+    return torch.cat(outs, 1)
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c2", "c3", "c4_tile", "c5_w768", "c5_c128_w768"])
 def test_full_size_properties(sa, cfg):
     """BASELINE configs at full size through size-independent properties (the oracle would take
     minutes here): (1) integer coords + tap k=0 at level 0 gathers the volume itself; (2) the
     lookup is linear in the volume; (3) a constant volume looks up to a constant inside the
     image; (4) pyramid levels are exact means of level 0; (5) TF32 corr matches an fp64 dot
     product on sampled entries."""
-    b, c, h, w = {"c1": (1, 256, 96, 128), "c2": (8, 256, 96, 312)}[cfg]
+    b, c, h, w = {"c1": (1, 256, 96, 128), "c2": (8, 256, 96, 312), "c3": (8, 256, 136, 240),
+                  "c4_tile": (1, 256, 280, 168), "c5_w768": (1, 256, 96, 768), "c5_c128_w768": (1, 128, 96, 768)}[cfg]
     gen = torch.Generator(device=DEV).manual_seed(0)
     fl = torch.randn(b, c, h, w, device=DEV, generator=gen)
     fr = torch.randn(b, c, h, w, device=DEV, generator=gen)
@@ -344,7 +368,7 @@ def test_full_size_properties(sa, cfg):
     hh = (idx // (w * w)) % h
     w2 = (idx // w) % w
     w3 = idx % w
-    ref = (fl[bb, :, hh, w2].double() * fr[bb, :, hh, w3].double()).sum(1) / 16.0
+    ref = (fl[bb, :, hh, w2].double() * fr[bb, :, hh, w3].double()).sum(1) / float(np.float32(np.sqrt(c)))
     got = vol.view(-1)[idx].double()
     assert float((got - ref).abs().max() / vol.abs().max()) < 1e-3
     blk = sa.CorrBlockB200(vol, num_levels=4, radius=4)
@@ -365,6 +389,11 @@ def test_full_size_properties(sa, cfg):
     # (2) linearity
     coords = torch.cat([tgt - torch.rand(b, 1, h, w, device=DEV, generator=gen) * 40, torch.zeros_like(tgt)], 1)
     o1 = blk(coords)
+    # (7) sampled pixels against the float64 closed form of the lookup (borders included: x - U(0, 40) leaves the row)
+    pix = torch.randint(0, b * h * w, (4096,), device=DEV, generator=gen)
+    want_px = sampled_closed_lookup(vol.view(b * h * w, w)[pix], coords[:, 0].reshape(-1)[pix])
+    got_px = o1.permute(0, 2, 3, 1).reshape(b * h * w, 36)[pix].double()
+    assert float((got_px - want_px).abs().max()) < 5e-6 * max(1.0, float(vol.abs().max()))
     blk2 = sa.CorrBlockB200(vol * 2.0 + 1.0, num_levels=4, radius=4)
     ones = sa.CorrBlockB200(torch.ones_like(vol), num_levels=4, radius=4)
     o2 = blk2(coords)
@@ -384,6 +413,17 @@ def test_full_size_properties(sa, cfg):
     nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w, device=DEV, generator=gen), dim=1)
     nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w, device=DEV, generator=gen), dim=1)
     assert torch.equal(sa.CorrBlockB200.from_normals(nl, nr)._ensure_packed(), sa.CorrBlockB200(sa.CorrBlockB200.mono_corr(nl, nr))._packed)
+    # (8) the benchmarked pair (fused stereo block + factored mono block, one launch) on sampled pixels vs float64
+    fs = sa.CorrBlockB200.from_features(fl, fr, truncate=(tdisp, tconf, 0.9))
+    fm = sa.CorrBlockB200.from_normals(nl, nr)
+    s_, m_ = sa.CorrBlockB200.lookup_pair(fs, fm, coords)
+    xs = coords[:, 0].reshape(-1)[pix]
+    mono_rows = sa.CorrBlockB200.mono_corr(nl, nr).view(b * h * w, w)[pix]
+    got_m = m_.permute(0, 2, 3, 1).reshape(b * h * w, 36)[pix].double()
+    assert float((got_m - sampled_closed_lookup(mono_rows, xs)).abs().max()) < 5e-6
+    t_rows = sa.truncation_mask(tdisp, tconf, 0.9, vol=vol.squeeze(3).unsqueeze(1)).view(b * h * w, w)[pix]
+    got_s = s_.permute(0, 2, 3, 1).reshape(b * h * w, 36)[pix].double()
+    assert float((got_s - sampled_closed_lookup(t_rows, xs)).abs().max()) < 5e-6 * max(1.0, float(vol.abs().max()))
 
 
 def test_lookup_fused_with_convc1(sa):

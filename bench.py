@@ -457,13 +457,27 @@ def run_gpu(args):
     n_lk_launch = m["n_lk_launch"]
     clocks = sampler.stop() if rank == 0 else None
 
+    # the collective's result, checked on NCCL hardware: one more gather of this rank's final disparity; rank 0
+    # compares every slice it received with what the owning rank sent (each rank ships a checksum of its slice)
+    gather_check = None
+    if dist is not None:
+        last = disp_bufs[(step_no[0] - 1) & 1].clone()
+        full = torch.empty((world * b, 1, h, w), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(full, last)
+        sums = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(sums, last.double().abs().sum().reshape(1))
+        got = full.view(world, -1).double().abs().sum(1)
+        gather_check = {"own_slice_equal": bool(torch.equal(full[rank * b:(rank + 1) * b], last)),
+                        "max_rel_checksum_diff": float(((got - sums).abs() / sums.clamp(min=1e-30)).max())}
+        assert gather_check["own_slice_equal"] and gather_check["max_rel_checksum_diff"] < 1e-12, gather_check
+
     # ---- the other two wirings of the same workload, same run (driver-measured) -------------------
     variants = None
     if args.extras and args.workload == DEFAULT_WORKLOAD and args.variant == "fused" and args.mono == "factored":
         torch.cuda.empty_cache()
-        va = measure_path(sa, d, "fused", "aggregated", 5, 3, args.graph)
+        va = measure_path(sa, d, "fused", "aggregated", 5, 3, args.graph, barrier=barrier)
         torch.cuda.empty_cache()
-        vp = measure_path(sa, d, "protocol", "packed", 5, 3, args.graph)
+        vp = measure_path(sa, d, "protocol", "packed", 5, 3, args.graph, barrier=barrier)
         torch.cuda.empty_cache()
         variants = {
             "aggregated_mono_ms": round(maxr(va["ms_step"]), 4),
@@ -558,7 +572,11 @@ def run_gpu(args):
     tiled = None
     if args.extras and args.tiled:
         torch.cuda.empty_cache()
-        tiled = tiled_measure(sa, dev, rank, world, dist, args, steps=max(5, min(args.steps, 20)), warmup=3)
+        try:
+            tiled = tiled_measure(sa, dev, rank, world, dist, args, steps=max(5, min(args.steps, 20)), warmup=3)
+        except Exception as e:   # reported in the line; the headline of this run stands on its own
+            tiled = {"error": f"{type(e).__name__}: {e}"}
+            print(f"[bench] tiled_c4 failed: {tiled['error']}", file=sys.stderr)
 
     result = None
     if rank == 0:
@@ -637,6 +655,7 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": roof,
             "kernels": kernels,
+            "gather_check": gather_check,
             "variants": variants,
             "tiled_c4": tiled,
             "cpu_baseline": cpu,
@@ -729,8 +748,22 @@ def tiled_measure(sa, dev, rank, world, dist, args, steps, warmup):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def agree(ok, what):
+        """All ranks continue or all ranks raise: a failure on one rank must not leave the others in a barrier."""
+        if dist is not None:
+            t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = bool(t.item())
+        if not ok:
+            raise RuntimeError(what)
+
     try:
-        st = tiling.SlotStitcher(images, H, W, work, dev)
+        st, err = None, ""
+        try:
+            st = tiling.SlotStitcher(images, H, W, work, dev)
+        except Exception as e:  # symmetric memory unavailable on this box, ...
+            err = f"{type(e).__name__}: {e}"
+        agree(st is not None, f"SlotStitcher could not be set up on every rank ({err or 'another rank failed'})")
         mine = st.my_units()
         # ---- correctness before speed: N ranks against one rank, and against the host stitch -----------------
         step(st, mine)
@@ -765,8 +798,9 @@ def tiled_measure(sa, dev, rank, world, dist, args, steps, warmup):
             del acc, host, alone
             if world > 1:
                 del solo
-            assert check["n_rank_vs_1_rank_max_abs"] <= 1e-4 and check["vs_host_stitch_max_abs"] <= 1e-3 * max(
-                1.0, check["mean_abs_disparity"]), f"tile stitch is wrong: {check}"
+        good = check is None or (check["n_rank_vs_1_rank_max_abs"] <= 1e-4 and
+                                 check["vs_host_stitch_max_abs"] <= 1e-3 * max(1.0, check["mean_abs_disparity"]))
+        agree(good, f"tile stitch is wrong: {check}")
         barrier()
         for _ in range(max(warmup, 3)):
             step(st, mine)

@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(2 * kLcTile, 4) lookup_conv_kernel(const LcArg
   uint8_t* sB = base + 2 * kLcABytes;                   // 10 KB weights
   float* s_bias = reinterpret_cast<float*>(sB + kLcBBytes);
   float* s_x = s_bias + kLcN;
-  int* s_blk = reinterpret_cast<int*>(s_x + TILE);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(s_blk + TILE);
+  unsigned* s_line = reinterpret_cast<unsigned*>(s_x + TILE);   // chunk (16 B) index of the pixel's line, or ~0u
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_line + TILE);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -116,72 +116,81 @@ __global__ void __launch_bounds__(2 * kLcTile, 4) lookup_conv_kernel(const LcArg
   const long long ntiles = (long long)tiles_x * a.B;
   uint32_t phase = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int b = (int)(tile / tiles_x);
-    const int hw0 = (int)(tile - (long long)b * tiles_x) * TILE;
-  const int npx = min(TILE, a.HW - hw0);
-  const long long row0 = (long long)b * a.HW + hw0;
+    const unsigned b = (unsigned)(tile / tiles_x);
+    const unsigned hw0 = (unsigned)(tile - (long long)b * tiles_x) * TILE;
+  const int npx = min(TILE, a.HW - (int)hw0);
 
-  // FACT: {k n0, k n1, k n2, line offset} per pixel, in the 8 KB of the A operands that the line staging leaves free
+  // All global addressing: uniform 64-bit base + 32-bit index in 16-byte units (as lookup_packed_kernel, round 2).
+  // FACT: {k n0, k n1, k n2, chunk index of line (c = 0, h, blk)} per pixel, in the 8 KB of the A operands that the
+  // line staging leaves free
   float4* s_n = reinterpret_cast<float4*>(sA + 2 * TILE * 128);
   if (tid < TILE) {
     float x = 0.f;
     int blk = -1;
+    unsigned line = ~0u;
     float n0 = 0.f, n1 = 0.f, n2 = 0.f;
     if (tid < npx) {
-      x = __ldg(a.coords + (long long)b * a.coords_bstride + hw0 + tid);
+      x = __ldg(a.coords + (size_t)b * a.coords_bstride + hw0 + tid);
       if (FACT) {
-        const long long plane = (long long)a.H * a.Wimg;
-        const float* nlp = a.nl + (long long)b * 3 * plane + hw0 + tid;
+        const unsigned plane = (unsigned)a.H * a.Wimg;
+        const float* nlp = a.nl + (size_t)(b * 3 * plane + hw0 + tid);
         n0 = __ldg(nlp); n1 = __ldg(nlp + plane); n2 = __ldg(nlp + 2 * plane);
       }
       const float fl = fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
       const int q = ((int)fl >> 3) + 5;  // blocks start at q = -5 (csrc/packed.cu)
-      if (q >= 0 && q < a.nblk) blk = q;
+      if (q >= 0 && q < a.nblk) {
+        blk = q;
+        line = ((b * (unsigned)a.HW + hw0 + tid) * (unsigned)a.nblk + (unsigned)q) * 8u;
+      }
     }
     s_x[tid] = x;
-    s_blk[tid] = blk;
+    s_line[tid] = line;
     if (FACT) {  // a pixel without a line reads line 0 with zero coefficients
       const float k = blk >= 0 ? a.kscale : 0.f;
-      const int off = blk >= 0 ? (((hw0 + tid) / a.Wimg) * a.nblk + blk) * 32 : 0;
-      s_n[tid] = make_float4(n0 * k, n1 * k, n2 * k, __int_as_float(off));
+      const unsigned h0 = hw0 / (unsigned)a.Wimg;      // uniform; a pixel of the tile is a few rows further down
+      const unsigned t = hw0 - h0 * (unsigned)a.Wimg + tid;
+      unsigned hh = h0;
+      for (unsigned w = a.Wimg; w <= t; w += a.Wimg) ++hh;
+      const unsigned off = blk >= 0 ? (((b * 3u) * a.H + hh) * (unsigned)a.nblk + (unsigned)blk) * 8u : 0u;
+      s_n[tid] = make_float4(n0 * k, n1 * k, n2 * k, __uint_as_float(off));
     }
   }
   __syncthreads();
 
-  // ---- stage one packed line per (pixel, volume), chunk c of pixel p at chunk c ^ (p & 7)
+  // ---- stage one packed line per (pixel, volume), chunk c of pixel p at chunk c ^ (p & 7); pixels without a line
+  // are zero-filled by cp.async's src-size 0 form
   float* stage = reinterpret_cast<float*>(sA);
-  {  // as in lookup_packed_kernel: the 64-bit line addresses are formed once per pixel and shared by the volumes
+  {
     constexpr int UPS = THREADS / 8, SPV = 4;  // units per step, steps per volume
-    const int ch = tid & 7, u0 = tid >> 3;
-    long long goff[SPV];
+    const unsigned ch = tid & 7, u0 = tid >> 3;
+    const float4* p0 = reinterpret_cast<const float4*>(a.packed[0]);
+    const float4* p1 = reinterpret_cast<const float4*>(a.packed[1]);
 #pragma unroll
     for (int m = 0; m < SPV; ++m) {
-      const int pm = u0 + m * UPS;
-      const int blk = s_blk[pm];
-      goff[m] = blk >= 0 ? ((row0 + pm) * (long long)a.nblk + blk) * 32 + ch * 4 : -1;
-    }
+      const unsigned pm = u0 + m * UPS;
+      const unsigned line = s_line[pm];
+      const unsigned ok = line != ~0u ? 16u : 0u;
+      const unsigned idx = (line != ~0u ? line : 0u) + ch;
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      const int v = n / SPV, m = n % SPV;
-      if (FACT && v == 1) continue;
-      const int pm = u0 + m * UPS;
-      float* dst = stage + (v * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2);
-      if (goff[m] >= 0)
-        lc_cp_async16(dst, (v ? a.packed[1] : a.packed[0]) + goff[m]);
-      else
-        *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int v = 0; v < 2; ++v) {
+        if (FACT && v == 1) continue;
+        float* dst = stage + (v * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+                     "l"((v ? p1 : p0) + idx), "r"(ok)
+                     : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     if (FACT) {  // the mono line = three right-normal lines combined with the pixel's scaled left normal
-      const int cplane = a.H * a.nblk * 32;
-      const float* rp = a.packed[1] + (long long)b * 3 * cplane + ch * 4;
+      const unsigned cplane = (unsigned)a.H * a.nblk * 8u;
+      const float4* rp = reinterpret_cast<const float4*>(a.packed[1]);
       float4 r[SPV][3], nn[SPV];
 #pragma unroll
       for (int m = 0; m < SPV; ++m) {
         nn[m] = s_n[u0 + m * UPS];
-        const int off = __float_as_int(nn[m].w);
+        const unsigned off = __float_as_uint(nn[m].w) + ch;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) r[m][c] = __ldg(reinterpret_cast<const float4*>(rp + (off + c * cplane)));
+        for (int c = 0; c < 3; ++c) r[m][c] = __ldg(rp + (off + c * cplane));
       }
 #pragma unroll
       for (int m = 0; m < SPV; ++m) {
@@ -295,7 +304,7 @@ __global__ void __launch_bounds__(2 * kLcTile, 4) lookup_conv_kernel(const LcArg
   // ---- epilogue: warp w reads TMEM lanes 32*(w%4).. (its pixels), columns of its volume (w/4)
   const int vq = warp >> 2, quarter = warp & 3;
   const int px = quarter * 32 + lane;
-  float* outp = (vq ? a.out[1] : a.out[0]) + ((long long)b * kLcN) * a.HW + hw0 + px;
+  float* outp = (vq ? a.out[1] : a.out[0]) + ((size_t)b * kLcN * a.HW + hw0 + px);
   const bool live = px < npx;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
@@ -314,7 +323,7 @@ __global__ void __launch_bounds__(2 * kLcTile, 4) lookup_conv_kernel(const LcArg
 #pragma unroll
       for (int c = 0; c < 32; ++c) {
         const int n = half * 32 + c;
-        st_stream_f32(outp + (long long)n * a.HW, fmaxf(__uint_as_float(r[c]) + s_bias[n], 0.0f));
+        st_stream_f32(outp + (unsigned)(n * a.HW), fmaxf(__uint_as_float(r[c]) + s_bias[n], 0.0f));
       }
     }
   }
@@ -350,6 +359,8 @@ extern "C" int sa_lookup_packed_conv(const float* packed_a, const float* packed_
   SA_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 31), SA_E_INVALID,
              "sa_lookup_packed_conv: bad sizes");
   SA_REQUIRE(W3 >= 8 && W3 % 8 == 0, SA_E_UNSUPPORTED, "sa_lookup_packed_conv: W3 must be a multiple of 8");
+  SA_REQUIRE((long long)B * H * W * (W3 / 8 + 9) < (1ll << 29) && (long long)B * 64 * H * W < (1ll << 32), SA_E_UNSUPPORTED,
+             "sa_lookup_packed_conv: arrays of 64 GB or more (32-bit chunk indices)");
   SA_REQUIRE(aligned16(packed_a) && aligned16(packed_b), SA_E_ALIGN, "sa_lookup_packed_conv: packed arrays must be 16-byte aligned");
   LcArgs a = {};
   a.packed[0] = packed_a; a.packed[1] = packed_b;
@@ -372,6 +383,8 @@ extern "C" int sa_lookup_factored_conv(const float* packed_a, const float* packe
   SA_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 31) && divisor != 0.f, SA_E_INVALID,
              "sa_lookup_factored_conv: bad sizes");
   SA_REQUIRE(W3 >= 8 && W3 % 8 == 0, SA_E_UNSUPPORTED, "sa_lookup_factored_conv: W3 must be a multiple of 8");
+  SA_REQUIRE((long long)B * H * W * (W3 / 8 + 9) < (1ll << 29) && (long long)B * 64 * H * W < (1ll << 32), SA_E_UNSUPPORTED,
+             "sa_lookup_factored_conv: arrays of 64 GB or more (32-bit chunk indices)");
   SA_REQUIRE(aligned16(packed_a) && aligned16(packed_normals_r), SA_E_ALIGN,
              "sa_lookup_factored_conv: packed arrays must be 16-byte aligned");
   LcArgs a = {};

@@ -58,11 +58,15 @@ for c, w in points:
     packed_bytes = p * (w // 8 + 9) * 128
     corr_bytes = 2 * b * c * H * w * 4 + packed_bytes            # bytes the fused kernel really moves
     corr_alg = 2 * b * c * H * w * 4 + 1.875 * p * w * 4         # volume + pooled levels written once
-    line = {"C": c, "W4": w, "B": b, "n_gpus": world,
+    factored = B_.mono_mode == "factored"
+    mono_bytes = (3 * b * H * (w // 8 + 9) * 128 + 3 * b * H * w * 4) if factored else packed_bytes
+    lk_alg, lk_real = (464, 432) if factored else (612, 544)    # bytes per pixel of a dual lookup
+    line = {"C": c, "W4": w, "B": b, "n_gpus": world, "mono": B_.mono_mode,
             "corr_pack_us": round(t_corr, 1), "corr_pack_gbs": round(corr_bytes / t_corr / 1e3, 0), "corr_pack_frac": round(corr_bytes / t_corr / 1e3 / peak, 3),
             "corr_pack_alg_frac": round(corr_alg / t_corr / 1e3 / peak, 3), "corr_tflops": round(2 * p * w * c / t_corr / 1e6, 1),
-            "mono_pack_us": round(t_mono, 1), "mono_pack_frac": round(packed_bytes / t_mono / 1e3 / peak, 3),
-            "lookup2_us": round(t_lk, 2), "lookup2_alg_frac": round(612 * p / t_lk / 1e3 / peak, 3), "lookup2_real_frac": round(544 * p / t_lk / 1e3 / peak, 3)}
+            "mono_pack_us": round(t_mono, 1), "mono_pack_frac": round(mono_bytes / t_mono / 1e3 / peak, 3),
+            "lookup2_us": round(t_lk, 2), "lookup2_alg_frac": round(lk_alg * p / t_lk / 1e3 / peak, 3),
+            "lookup2_real_frac": round(lk_real * p / t_lk / 1e3 / peak, 3)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     del fs, fm, d, g, o

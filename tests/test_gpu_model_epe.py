@@ -192,6 +192,34 @@ def test_real_model_epe_pure_ramp_with_the_lsq_stage_held(variant):
     assert epe_free < max(GATE_PX, 5 * epe_ulp) + 0.25, "un-held difference far above the reference's own sensitivity"
 
 
+@pytest.mark.parametrize("variant", ["protocol", "fused"])
+def test_real_model_under_mixed_precision_autocast(variant):
+    """The reference's `--mixed_precision` mode (test.py:63,189: the whole forward under fp16 autocast): the hourglass /
+    classifier volumes handed to the block constructor are fp16 there.  Both runs are under the same autocast; the
+    B200 block must accept what `CorrBlock1D` accepts and stay inside the gate."""
+    sa_mod, model, B, integration = _setup({})
+    inputs = _inputs(384, 512)
+
+    def fwd():
+        random.seed(0)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            disp, _ = model(*inputs, iters=32, test_mode=True)
+        torch.cuda.synchronize()
+        return disp.float()
+
+    d_ref = fwd()
+    try:
+        integration.install(sa_mod, fused=(variant == "fused"))
+        d_b200 = fwd()
+    finally:
+        integration.uninstall(sa_mod)
+    assert torch.isfinite(d_ref).all() and torch.isfinite(d_b200).all()
+    epe = float((d_b200 - d_ref).abs().mean())
+    print(f"[autocast fp16, {variant}] EPE {epe:.2e} px (max {float((d_b200 - d_ref).abs().max()):.2e}); "
+          f"mean |disp| {float(d_ref.abs().mean()):.3f} px")
+    assert epe < GATE_PX, f"EPE {epe} px exceeds the {GATE_PX} px gate"
+
+
 def test_half_precision_volume_and_maps():
     """Under the reference's --mixed_precision autocast (test.py:63,189) the hourglass / classifier volumes and the
     truncation maps arrive in fp16; `CorrBlock1D` takes any dtype (bilinear_sampler casts, utils/utils.py:19-35)."""

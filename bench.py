@@ -284,12 +284,13 @@ def _ev():
     return torch.cuda.Event(enable_timing=True)
 
 
-def measure_path(sa, d, variant, mono, steps, warmup, graph, after_step=None, drain=None, barrier=None):
+def measure_path(sa, d, variant, mono, steps, warmup, graph, after_step=None, drain=None, barrier=None, storage="fp32"):
     """Time `steps` steps of the path on device-resident inputs `d` (CUDA events on the current stream).
     Returns ms per step, ms per lookup launch, launches per step, and (fused + graph) the two builders timed alone."""
     B = sa.CorrBlockB200
-    saved_mode = B.mono_mode
+    saved_mode, saved_storage = B.mono_mode, B.storage
     B.mono_mode = mono if mono != "aggregated" else "packed"
+    B.storage = storage
     otf = variant == "fused" and mono == "otf"
     path = GpuPath(sa, d, variant, mono)
     out = None
@@ -378,7 +379,7 @@ def measure_path(sa, d, variant, mono, steps, warmup, graph, after_step=None, dr
         return {"ms_step": ms_total / steps, "lk_launch_ms": lk_ms / n_lk, "n_lk_launch": n_lk, "launches": launches,
                 "breakdown": breakdown}
     finally:
-        B.mono_mode = saved_mode
+        B.mono_mode, B.storage = saved_mode, saved_storage
 
 
 def init_dist():
@@ -452,7 +453,7 @@ def run_gpu(args):
                 pending[i] = None
 
     m = measure_path(sa, d, args.variant, args.mono, args.steps, args.warmup, args.graph, after_step=collective,
-                     drain=drain, barrier=barrier)
+                     drain=drain, barrier=barrier, storage=args.storage)
     ms_total, lk_launch_ms, launches, breakdown = m["ms_step"] * args.steps, m["lk_launch_ms"], m["launches"], m["breakdown"]
     n_lk_launch = m["n_lk_launch"]
     clocks = sampler.stop() if rank == 0 else None
@@ -479,9 +480,16 @@ def run_gpu(args):
         torch.cuda.empty_cache()
         vp = measure_path(sa, d, "protocol", "packed", 5, 3, args.graph, barrier=barrier)
         torch.cuda.empty_cache()
+        vh = measure_path(sa, d, "fused", "factored", 5, 3, args.graph, barrier=barrier, storage="fp16")
+        torch.cuda.empty_cache()
         variants = {
             "aggregated_mono_ms": round(maxr(va["ms_step"]), 4),
             "protocol_ms": round(maxr(vp["ms_step"]), 4),
+            "fp16_storage_ms": round(maxr(vh["ms_step"]), 4),
+            "fp16_storage": "opt-in (CorrBlockB200.storage = 'fp16'): the headline wiring with the stereo block's packed pyramid "
+                            "stored in fp16 (the fp32 values rounded to nearest: +3e-4 of max|V|, inside the TF32 tolerance); "
+                            f"corr_pack {round(vh['breakdown'][0] * 1e3, 1) if vh['breakdown'] else None} us, "
+                            f"lookup {round(vh['lk_launch_ms'] * 1e3, 2)} us",
             "steps": 5,
             "aggregated_mono": "README wiring (--use_aggregate_mono_vol, stereoanywhere.py:162-165,210,257-259): mono volume "
                                "materialised, mono block built from a dense volume (sa_pack_pyramid), dual packed lookup",
@@ -493,6 +501,7 @@ def run_gpu(args):
     # Every step uploads ITS OWN inputs from pinned host memory and reads its result back; the
     # upload of step k+1 runs on a copy stream while step k computes (two device buffer sets).
     sa.CorrBlockB200.mono_mode = args.mono if args.mono != "aggregated" else "packed"
+    sa.CorrBlockB200.storage = args.storage
     keys = ["fl", "fr", "nl", "nr", "coords0", "delta", "tdisp", "tconf"]
     sets = [{k: torch.empty_like(d[k]) for k in keys} for _ in range(2)]
     res_s = torch.empty((b, LEVELS * (2 * RADIUS + 1), h, w), dtype=torch.float32).pin_memory()
@@ -604,8 +613,8 @@ def run_gpu(args):
         if breakdown is not None:
             st_us = breakdown[0] * 1e3
             mo_us = breakdown[1] * 1e3 if breakdown[1] is not None else None
-            packed = p * (w // 8 + 9) * 128
-            mono_bytes = 3 * b * h * (w // 8 + 9) * 128 + 3 * b * h * w * 4 if factored else packed
+            packed = p * (w // 8 + 9) * (128 if args.storage == "fp32" else 64)
+            mono_bytes = 3 * b * h * (w // 8 + 9) * 128 + 3 * b * h * w * 4 if factored else p * (w // 8 + 9) * 128
             if args.mono == "aggregated":   # volume written, read again, packed
                 mono_bytes = 2 * p * w * 4 + packed
             tf32_peak = tensor_peak_tf32()
@@ -637,7 +646,7 @@ def run_gpu(args):
             "scaling": "weak", "vs_baseline": None, "dtype": f"{args.precision} corr (fp32 accumulate), f32 pyramid/lookup",
             "data": "synthetic (seeded N(0,1) features, unit normals, U(0,W/4) disparities)",
             "config": workload_config(args.workload, world),
-            "impl_config": {"variant": args.variant, "cuda_graph": bool(args.graph),
+            "impl_config": {"variant": args.variant, "cuda_graph": bool(args.graph), "storage": args.storage,
                             "mono": ("on the fly: lookups computed from the normal maps inside the lookup kernel, bit-identical to "
                                      "the packed pyramid (no mono volume / pyramid in memory)") if otf else
                                     ("factored: packed pyramid of the right normal map's rows (rank-3 volume, linear pyramid); "
@@ -985,6 +994,8 @@ def main():
                     help="mono block of the fused variant: factored (packed right normals, combined inside the lookup), "
                          "the packed pyramid of the volume, lookups computed on the fly from the normals, or 'aggregated': "
                          "the README configuration, block built from a dense (hourglass-output-like) volume")
+    ap.add_argument("--storage", default="fp32", choices=["fp32", "fp16", "bf16"],
+                    help="storage of the stereo block's packed pyramid (fused variant): fp32 (default) or the opt-in 16-bit modes")
     ap.add_argument("--graph", type=int, default=1, help="replay the step from a CUDA graph in the device-resident run")
     ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -162,6 +162,14 @@ int sa_lookup_packed_factored(const float* packed_a, const float* packed_normals
 int sa_corr_pack_tf32(const float* fmap_l, const float* fmap_r, int B, int C, int H, int W2, int W3, float divisor,
                       float post_scale, const float* trunc_disp, const float* trunc_conf, double trunc_gain,
                       float* packed, void* stream);
+/* The same kernel with the packed pyramid stored in 16 bits (half_kind 1 = fp16, 2 = bf16; round to nearest even):
+ * lines of 64 bytes, element i of a line in the low (i even) / high (i odd) half of 32-bit word i / 2; packed_h is
+ * rows x (W3/8 + 9) x 64 bytes.  The arithmetic up to the rounding of the stored values is that of
+ * sa_corr_pack_tf32; read it with sa_lookup_packed_half.  Opt-in storage mode: fp16 adds at most 2^-11 = 4.9e-4 of
+ * max|vol| (inside the TF32 tolerance of 1e-3 together with the product's own ~3e-4), bf16 3.9e-3 (the 1e-2 class). */
+int sa_corr_pack_tf32_half(const float* fmap_l, const float* fmap_r, int B, int C, int H, int W2, int W3, float divisor,
+                           float post_scale, const float* trunc_disp, const float* trunc_conf, double trunc_gain,
+                           int half_kind, void* packed_h, void* stream);
 
 /* ---------------------------------------------------------------- lookup + motion-encoder front end
  * out_v[b,n,h,w] = relu(bias[n] + sum_k weight[n,k] * lookup_v[b,k,h,w]) for the stereo and the mono volume
@@ -219,6 +227,16 @@ int sa_lookup_backward(const float* grad_out, const float* coords, int64_t coord
 int sa_pyramid_backward(float* d0, const float* const* h_dlevels, const int* h_widths, const int64_t* h_pitches,
                         int num_levels, int64_t rows, const float* trunc_disp, const float* trunc_conf, double trunc_gain,
                         int w2_size, void* stream);
+
+/* ---------------------------------------------------------------- lookups from a 16-bit packed pyramid
+ * The lookup of sa_lookup_packed with volume A stored by sa_corr_pack_tf32_half (half_kind 1 = fp16, 2 = bf16): the
+ * stored values are widened to fp32 and everything after that is sa_lookup_packed's arithmetic - the result equals,
+ * bit for bit, a lookup from the fp32 packed array holding the same (rounded) values.  mode_b selects the second
+ * volume of a dual lookup: 0 none (out_b NULL), 1 an fp32 packed pyramid (packed_b), 2 the factored mono volume
+ * (packed_b = packed right normals, normals_l / divisor / post_scale as in sa_lookup_packed_factored). */
+int sa_lookup_packed_half(const void* packed_h_a, int half_kind, int mode_b, const float* packed_b, const float* normals_l,
+                          float divisor, float post_scale, int W3, const float* coords, int64_t coords_bstride,
+                          float* out_a, float* out_b, int B, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------- config 4: tile stitch (no collective)
  * Replaces the accumulate / normalise of `TileWrapper` (mapreduce_v2/tile_wrapper.py:172-185, :206, :226-247,

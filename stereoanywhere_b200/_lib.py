@@ -49,6 +49,10 @@ def _declare(lib):
     lib.sa_lookup_packed.argtypes = [vp, vp, i, vp, i64, vp, vp, i, i, i, vp]
     lib.sa_corr_pack_tf32.restype = i
     lib.sa_corr_pack_tf32.argtypes = [vp, vp, i, i, i, i, i, f, f, vp, vp, d, vp, vp]
+    lib.sa_corr_pack_tf32_half.restype = i
+    lib.sa_corr_pack_tf32_half.argtypes = [vp, vp, i, i, i, i, i, f, f, vp, vp, d, i, vp, vp]
+    lib.sa_lookup_packed_half.restype = i
+    lib.sa_lookup_packed_half.argtypes = [vp, i, i, vp, vp, f, f, i, vp, i64, vp, vp, i, i, i, vp]
     lib.sa_volume_softargmax.restype = i
     lib.sa_volume_softargmax.argtypes = [vp, i64, i, i, vp, vp, vp]
     lib.sa_volume_entropy_conf.restype = i
@@ -85,7 +89,7 @@ def _declare(lib):
 
 EXPORTS = [
     "sa_abi_version", "sa_last_error", "sa_corr_fp32", "sa_corr_tf32", "sa_pyramid", "sa_lookup", "sa_lookup2",
-    "sa_truncate", "sa_masked_volume", "sa_corrupt", "sa_packed_row_floats", "sa_pack_pyramid", "sa_pack_pyramid_normals", "sa_lookup_packed", "sa_lookup_packed_conv", "sa_lookup_factored_conv", "sa_corr_pack_tf32", "sa_mono_inputs", "sa_weighted_lsq", "sa_stitch_tile", "sa_stitch_finish", "sa_lookup_packed_normals", "sa_lookup_packed_factored", "sa_corr_backward_tf32", "sa_lookup_backward", "sa_pyramid_backward", "sa_volume_softargmax", "sa_volume_entropy_conf",
+    "sa_truncate", "sa_masked_volume", "sa_corrupt", "sa_packed_row_floats", "sa_pack_pyramid", "sa_pack_pyramid_normals", "sa_lookup_packed", "sa_lookup_packed_conv", "sa_lookup_factored_conv", "sa_corr_pack_tf32", "sa_corr_pack_tf32_half", "sa_lookup_packed_half", "sa_mono_inputs", "sa_weighted_lsq", "sa_stitch_tile", "sa_stitch_finish", "sa_lookup_packed_normals", "sa_lookup_packed_factored", "sa_corr_backward_tf32", "sa_lookup_backward", "sa_pyramid_backward", "sa_volume_softargmax", "sa_volume_entropy_conf",
 ]
 
 

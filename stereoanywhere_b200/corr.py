@@ -187,6 +187,8 @@ class CorrBlockB200:
         self._truncate: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None
         self._levels: Optional[List[torch.Tensor]] = None     # 16-byte-pitched levels (general layout)
         self._packed: Optional[torch.Tensor] = None           # line-packed pyramid of the volume
+        self._packed_h: Optional[torch.Tensor] = None         # line-packed pyramid in 16-bit storage (from_features, `storage`)
+        self._half_kind = 0                                   # 1 = fp16, 2 = bf16 (of _packed_h)
         self._packed_nr: Optional[torch.Tensor] = None        # mono_mode "factored": packed rows of the right normals
         self._otf = False                                     # mono_mode "otf": lookups computed from the normals
         self._grad: Optional[_GradState] = None               # backward state (training only)
@@ -229,8 +231,20 @@ class CorrBlockB200:
     #: SA_B200_MONO overrides the default.
     mono_mode = os.environ.get("SA_B200_MONO", "factored")
 
+    #: storage of the packed pyramid written by `from_features`: "fp32" (default: 128-byte lines), "fp16" or "bf16"
+    #: (64-byte lines: `sa_corr_pack_tf32` writes half the bytes, 293 instead of 370 us at KITTI size, batch 8).  Opt-in:
+    #: the stored values are the fp32 ones rounded to nearest - fp16 adds at most 2^-11 = 4.9e-4 of max|V| (measured
+    #: 3.2e-4; together with the TF32 product still inside the 1e-3 tolerance), bf16 3.9e-3 (the 1e-2 class); the
+    #: lookup widens them and is otherwise unchanged.  SA_B200_STORAGE overrides the default.
+    storage = os.environ.get("SA_B200_STORAGE", "fp32")
+
     def _ensure_packed(self) -> torch.Tensor:
-        """The packed pyramid of this block (built on demand for on-the-fly / factored mono blocks)."""
+        """The fp32 packed pyramid of this block (built on demand for on-the-fly / factored mono blocks and for
+        stereo blocks held in 16-bit storage)."""
+        if self._packed is None and self._packed_h is not None:
+            t = self._truncate
+            self._packed = _OPS.corr_pack(self._features[0], self._features[1], t[0] if t else None, t[1] if t else None,
+                                          t[2] if t else 0.0)
         if self._packed is None and (self._otf or self._packed_nr is not None):
             self._packed = _OPS.pack_pyramid_normals(self._normals[0], self._normals[1], self._normals[2])
             self._otf = False
@@ -239,7 +253,8 @@ class CorrBlockB200:
 
     @classmethod
     def from_features(cls, fmap2: torch.Tensor, fmap3: torch.Tensor, num_levels: int = 4, radius: int = 4, *,
-                      truncate: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None) -> "CorrBlockB200":
+                      truncate: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None,
+                      storage: Optional[str] = None) -> "CorrBlockB200":
         """The stereo block of stereoanywhere.py:135 + :203 + :253-255 in ONE kernel: correlation on the tensor
         cores, truncation product and pyramid in the GEMM epilogue, written once as the packed pyramid
         (csrc/corr_pack_tcgen05.cu).  Same values, bit for bit, as
@@ -256,8 +271,16 @@ class CorrBlockB200:
         self._features = (fmap2.float(), fmap3.float())
         self._truncate = _truncate_args(truncate)
         t = self._truncate
-        self._packed = _OPS.corr_pack(self._features[0], self._features[1], t[0] if t else None, t[1] if t else None,
-                                      t[2] if t else 0.0)
+        storage = cls.storage if storage is None else storage
+        if storage == "fp32":
+            self._packed = _OPS.corr_pack(self._features[0], self._features[1], t[0] if t else None, t[1] if t else None,
+                                          t[2] if t else 0.0)
+        elif storage in ops.HALF_KINDS:   # opt-in 16-bit storage of the packed pyramid (see `storage`)
+            self._half_kind = ops.HALF_KINDS[storage][0]
+            self._packed_h = _OPS.corr_pack_half(self._features[0], self._features[1], t[0] if t else None,
+                                                 t[1] if t else None, t[2] if t else 0.0, self._half_kind)
+        else:
+            raise ValueError(f"storage must be 'fp32', 'fp16' or 'bf16' (got {storage!r})")
         return self
 
     def _source(self) -> torch.Tensor:
@@ -299,6 +322,8 @@ class CorrBlockB200:
             return _OPS.lookup_normals(self._normals[0], self._normals[1], self._normals[2], coords)
         if self._packed_nr is not None:
             return _OPS.lookup_factored(self._packed_nr, self._normals[0], self._normals[2], coords)
+        if self._packed_h is not None:
+            return _OPS.lookup_half(self._packed_h, self._half_kind, self._shape[3], coords)
         if self._packed is not None:
             return _OPS.lookup_packed(self._packed, self._shape[3], coords)
         return _OPS.lookup(self._levels, self._widths, coords, self.radius, self.pad[0], self.pad[1])
@@ -349,6 +374,11 @@ class CorrBlockB200:
         if torch.is_grad_enabled() and (block_a._handle is not None or block_b._handle is not None):
             return False  # training: each lookup is its own autograd node
         otf_b = block_b._otf or block_b._packed_nr is not None  # block_b holds no packed volume of its own
+        if block_a._packed_h is not None:   # 16-bit stereo block: with a factored or an fp32-packed partner
+            return (block_a._shape == block_b._shape and block_b.pad == [0, 0] and block_b._packed_h is None
+                    and not block_b._otf and (block_b._packed_nr is not None or block_b._packed is not None))
+        if block_b._packed_h is not None:
+            return False
         return not (block_a.radius != block_b.radius or block_a._widths != block_b._widths
                     or block_a._shape != block_b._shape
                     or block_a.pad != [0, 0] or block_b.pad != [0, 0] or block_a._otf
@@ -365,7 +395,14 @@ class CorrBlockB200:
         dt = coords.dtype
         if dt != torch.float32:
             coords = coords.float()
-        if block_a._packed is not None and fact_b:
+        if block_a._packed_h is not None:
+            if fact_b:
+                oa, ob = _OPS.lookup_half2(block_a._packed_h, block_a._half_kind, 2, block_b._packed_nr, block_b._normals[0],
+                                           block_b._normals[2], block_a._shape[3], coords)
+            else:
+                oa, ob = _OPS.lookup_half2(block_a._packed_h, block_a._half_kind, 1, block_b._packed, None, 1.0,
+                                           block_a._shape[3], coords)
+        elif block_a._packed is not None and fact_b:
             oa, ob = _OPS.lookup_packed_factored2(block_a._packed, block_b._packed_nr, block_b._normals[0],
                                                   block_b._normals[2], coords)
         elif block_a._packed is not None and block_b._otf:

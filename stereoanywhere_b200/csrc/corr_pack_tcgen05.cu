@@ -55,15 +55,19 @@ struct Args {
   float gain, one_minus_gain;
 };
 
-template <bool TRUNC>
+// HK = 0: fp32 lines (128 B); 1 / 2: fp16 / bf16 lines (64 B) - the packed array, the staging tiles and the TMA
+// stores shrink to half (opt-in storage mode; the fp32 arithmetic up to the rounding of the stored values is the same)
+template <bool TRUNC, int HK>
 __global__ void __launch_bounds__(kThreads, 1)
 corr_pack_tf32_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_constant__ CUtensorMap map_r,
                       const __grid_constant__ CUtensorMap map_o, const Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t stage_bytes = (uint32_t)(kBM / kBox + a.cpt) * kBoxBytes;
+  constexpr int kLineBytes = HK ? 64 : 128;
+  constexpr int kTileBytes = kBM * kLineBytes;
   uint8_t* stag = base;
-  uint8_t* pipe = base + kStagingBytes;
+  uint8_t* pipe = base + kNStg * kTileBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(pipe + (size_t)a.nstage * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
@@ -241,17 +245,25 @@ corr_pack_tf32_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_co
         asm volatile("bar.sync 1, 128;" ::: "memory");  // (they had this step's TMEM load + pooling to do so)
         if (live) {
           const int li = 4 * cc;
-          if (li + 0 < a.nblk) win.store_line<0>(stag + 0 * (kBM * 128) + row * 128, swz);
-          if (li + 1 < a.nblk) win.store_line<1>(stag + 1 * (kBM * 128) + row * 128, swz);
-          if (li + 2 < a.nblk) win.store_line<2>(stag + 2 * (kBM * 128) + row * 128, swz);
-          if (li + 3 < a.nblk) win.store_line<3>(stag + 3 * (kBM * 128) + row * 128, swz);
+          if (HK == 0) {
+            if (li + 0 < a.nblk) win.store_line<0>(stag + 0 * kTileBytes + row * 128, swz);
+            if (li + 1 < a.nblk) win.store_line<1>(stag + 1 * kTileBytes + row * 128, swz);
+            if (li + 2 < a.nblk) win.store_line<2>(stag + 2 * kTileBytes + row * 128, swz);
+            if (li + 3 < a.nblk) win.store_line<3>(stag + 3 * kTileBytes + row * 128, swz);
+          } else {
+            constexpr int K = HK ? HK : 1;
+            if (li + 0 < a.nblk) win.store_line_half<0, K>(stag + 0 * kTileBytes + row * 64, row);
+            if (li + 1 < a.nblk) win.store_line_half<1, K>(stag + 1 * kTileBytes + row * 64, row);
+            if (li + 2 < a.nblk) win.store_line_half<2, K>(stag + 2 * kTileBytes + row * 64, row);
+            if (li + 3 < a.nblk) win.store_line_half<3, K>(stag + 3 * kTileBytes + row * 64, row);
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (et == 0) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (4 * cc + j < a.nblk) tma_store_4d(&map_o, stag + j * (kBM * 128), 0, 4 * cc + j, m0, bh);
+            if (4 * cc + j < a.nblk) tma_store_4d(&map_o, stag + j * kTileBytes, 0, 4 * cc + j, m0, bh);
           tma_commit();
         }
         if (live) win.advance(v);
@@ -270,11 +282,12 @@ corr_pack_tf32_kernel(const __grid_constant__ CUtensorMap map_l, const __grid_co
 }  // namespace cpk
 }  // namespace sa
 
-extern "C" int sa_corr_pack_tf32(const float* fmap_l, const float* fmap_r, int B, int C, int H, int W2, int W3,
-                                 float divisor, float post_scale, const float* trunc_disp, const float* trunc_conf,
-                                 double trunc_gain, float* packed, void* stream) {
-  using namespace sa;
-  using namespace sa::cpk;
+namespace sa {
+namespace cpk {
+
+static int launch_corr_pack(const float* fmap_l, const float* fmap_r, int B, int C, int H, int W2, int W3, float divisor,
+                            float post_scale, const float* trunc_disp, const float* trunc_conf, double trunc_gain,
+                            void* packed, int hk, cudaStream_t stream) {
   SA_REQUIRE(fmap_l && fmap_r && packed, SA_E_INVALID, "sa_corr_pack_tf32: null pointer");
   SA_REQUIRE(B > 0 && C > 0 && H > 0 && W2 > 0 && W3 > 0, SA_E_INVALID, "sa_corr_pack_tf32: sizes must be positive");
   SA_REQUIRE(divisor != 0.f, SA_E_INVALID, "sa_corr_pack_tf32: divisor == 0");
@@ -286,6 +299,7 @@ extern "C" int sa_corr_pack_tf32(const float* fmap_l, const float* fmap_r, int B
   SA_REQUIRE((long long)B * H <= 0x7fffffffLL, SA_E_UNSUPPORTED, "sa_corr_pack_tf32: B*H too large");
   SA_REQUIRE(aligned16(fmap_l) && aligned16(fmap_r) && aligned16(packed), SA_E_ALIGN,
              "sa_corr_pack_tf32: pointers must be 16-byte aligned");
+  SA_REQUIRE(hk >= 0 && hk <= 2, SA_E_INVALID, "sa_corr_pack_tf32: storage kind must be 0 (fp32), 1 (fp16) or 2 (bf16)");
 
   Args a = {};
   a.C = C; a.H = H; a.W2 = W2; a.W3 = W3;
@@ -296,8 +310,10 @@ extern "C" int sa_corr_pack_tf32(const float* fmap_l, const float* fmap_r, int B
   a.cpt = (a.nch + a.n_tiles - 1) / a.n_tiles;
   a.nblk = W3 / 8 + 9;
   a.n_steps = (a.nblk - 1) / 4 + 1;
+  const int line_bytes = hk ? 64 : 128;
+  const int staging = kNStg * kBM * line_bytes;
   const int stage_bytes = (kBM / kBox + a.cpt) * kBoxBytes;
-  a.nstage = (kSmemBudget - kStagingBytes) / stage_bytes;
+  a.nstage = (kSmemBudget - staging) / stage_bytes;
   if (a.nstage > kMaxStages) a.nstage = kMaxStages;
   SA_REQUIRE(a.nstage >= 2, SA_E_UNSUPPORTED, "sa_corr_pack_tf32: tile does not fit shared memory");
   a.stripes = (long long)B * H * a.m_tiles;
@@ -319,21 +335,43 @@ extern "C" int sa_corr_pack_tf32(const float* fmap_l, const float* fmap_r, int B
     int rc = make_map(&mr, fmap_r, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, "fmap_r");
     if (rc) return rc;
   }
-  {
-    cuuint64_t dims[4] = {32, (cuuint64_t)a.nblk, (cuuint64_t)W2, (cuuint64_t)B * H};
-    cuuint64_t str[3] = {128, (cuuint64_t)a.nblk * 128, (cuuint64_t)W2 * a.nblk * 128};
-    cuuint32_t box[4] = {32, 1, kBM, 1};
-    int rc = make_map(&mo, packed, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "packed");
+  {  // lines as 32-bit words: 32 per line (fp32) or 16 (two 16-bit values per word)
+    const cuuint64_t lb = (cuuint64_t)line_bytes;
+    cuuint64_t dims[4] = {lb / 4, (cuuint64_t)a.nblk, (cuuint64_t)W2, (cuuint64_t)B * H};
+    cuuint64_t str[3] = {lb, (cuuint64_t)a.nblk * lb, (cuuint64_t)W2 * a.nblk * lb};
+    cuuint32_t box[4] = {(cuuint32_t)(lb / 4), 1, kBM, 1};
+    int rc = make_map(&mo, packed, 4, dims, str, box, hk ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, "packed");
     if (rc) return rc;
   }
-  const size_t smem = 1024 + kStagingBytes + (size_t)a.nstage * stage_bytes + (2 * kMaxStages + 5) * sizeof(uint64_t);
+  const size_t smem = 1024 + staging + (size_t)a.nstage * stage_bytes + (2 * kMaxStages + 5) * sizeof(uint64_t);
   const bool trunc = trunc_disp != nullptr;
-  auto kern = trunc ? corr_pack_tf32_kernel<true> : corr_pack_tf32_kernel<false>;
+  void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const Args) =
+      hk == 0 ? (trunc ? corr_pack_tf32_kernel<true, 0> : corr_pack_tf32_kernel<false, 0>)
+      : hk == 1 ? (trunc ? corr_pack_tf32_kernel<true, 1> : corr_pack_tf32_kernel<false, 1>)
+                : (trunc ? corr_pack_tf32_kernel<true, 2> : corr_pack_tf32_kernel<false, 2>);
   {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) SA_FAIL((int)e, "sa_corr_pack_tf32: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   }
   const long long grid = a.stripes < (long long)num_sms() ? a.stripes : (long long)num_sms();
-  kern<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(ml, mr, mo, a);
+  kern<<<(unsigned)grid, kThreads, smem, stream>>>(ml, mr, mo, a);
   return finish_launch("sa_corr_pack_tf32");
+}
+
+}  // namespace cpk
+}  // namespace sa
+
+extern "C" int sa_corr_pack_tf32(const float* fmap_l, const float* fmap_r, int B, int C, int H, int W2, int W3,
+                                 float divisor, float post_scale, const float* trunc_disp, const float* trunc_conf,
+                                 double trunc_gain, float* packed, void* stream) {
+  return sa::cpk::launch_corr_pack(fmap_l, fmap_r, B, C, H, W2, W3, divisor, post_scale, trunc_disp, trunc_conf, trunc_gain,
+                                   packed, 0, (cudaStream_t)stream);
+}
+
+extern "C" int sa_corr_pack_tf32_half(const float* fmap_l, const float* fmap_r, int B, int C, int H, int W2, int W3,
+                                      float divisor, float post_scale, const float* trunc_disp, const float* trunc_conf,
+                                      double trunc_gain, int half_kind, void* packed_h, void* stream) {
+  SA_REQUIRE(half_kind == 1 || half_kind == 2, SA_E_INVALID, "sa_corr_pack_tf32_half: half_kind must be 1 (fp16) or 2 (bf16)");
+  return sa::cpk::launch_corr_pack(fmap_l, fmap_r, B, C, H, W2, W3, divisor, post_scale, trunc_disp, trunc_conf, trunc_gain,
+                                   packed_h, half_kind, (cudaStream_t)stream);
 }

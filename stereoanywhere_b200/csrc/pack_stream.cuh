@@ -15,10 +15,33 @@
 // pyramid's own 0.5 * (a + b) (reference corr.py:88-91), so the lines equal those of pack_kernel bit for bit.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "sa_common.cuh"
 
 namespace sa {
+
+// two floats -> one word of 16-bit storage (lo in bits 0..15), and back
+template <int HK>
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+  if (HK == 1) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <int HK>
+__device__ __forceinline__ void unpack_half2(uint32_t w, float& lo, float& hi) {
+  if (HK == 1) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = f.x; hi = f.y;
+  } else {
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xffff0000u);
+  }
+}
 
 struct PackWindow {
   float P[44], H1[40], H2[22], H3[13];
@@ -55,6 +78,24 @@ struct PackWindow {
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       *reinterpret_cast<float4*>(dst_row + ((k ^ swz) << 4)) = make_float4(ln[4 * k], ln[4 * k + 1], ln[4 * k + 2], ln[4 * k + 3]);
+  }
+  // the same line in 16-bit storage (HK = 1: fp16, 2: bf16; round to nearest even): 64 bytes, element i in the low /
+  // high half of word i >> 1, written 64B-swizzled for a TMA store (chunk k of row r lands at chunk k ^ ((r >> 1) & 3))
+  template <int J, int HK>
+  __device__ __forceinline__ void store_line_half(uint8_t* dst_row, int row) const {
+    float ln[32];
+#pragma unroll
+    for (int s = 0; s < 17; ++s) ln[s] = P[8 * J + s];
+    ln[17] = H1[4 * J]; ln[18] = H1[4 * J + 1]; ln[19] = H1[4 * J + 10]; ln[20] = H1[4 * J + 11]; ln[21] = H1[4 * J + 12];
+    ln[22] = H2[2 * J]; ln[23] = H2[2 * J + 1]; ln[24] = H2[2 * J + 8]; ln[25] = H2[2 * J + 9]; ln[26] = H2[2 * J + 10];
+    ln[27] = H3[J]; ln[28] = H3[J + 1]; ln[29] = H3[J + 7]; ln[30] = H3[J + 8]; ln[31] = H3[J + 9];
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = pack_half2<HK>(ln[2 * i], ln[2 * i + 1]);
+    const int sw = (row >> 1) & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      *reinterpret_cast<uint4*>(dst_row + ((k ^ sw) << 4)) = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
   }
   // slide the window by one chunk
   __device__ __forceinline__ void advance(const float (&v)[32]) {

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "pack_stream.cuh"
 #include "sa_common.cuh"
 #include "tc_common.cuh"
 
@@ -255,6 +256,34 @@ __device__ __forceinline__ void line_levels(const float* src, int p, float (&l0)
   for (int t = 0; t < 5; ++t) l3[2 + t] = (l2[2 * t] + l2[2 * t + 1]) * 0.5f;
 }
 
+// The same from a line in 16-bit storage (HK = 1: fp16, 2: bf16; csrc/corr_pack_tcgen05.cu, sa_corr_pack_tf32_half):
+// 64 bytes in the half of the pixel's 128-byte slot selected by p & 1, chunk c at c ^ ((p >> 1) & 3).
+template <int HK>
+__device__ __forceinline__ void line_levels_half(const float* slot, int p, float (&l0)[17], float (&l1)[13], float (&l2)[11],
+                                                 float (&l3)[10]) {
+  float ln[32];
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(slot) + ((p & 1) << 6);
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    const uint4 t = *reinterpret_cast<const uint4*>(src + ((ch ^ ((p >> 1) & 3)) << 4));
+    unpack_half2<HK>(t.x, ln[8 * ch], ln[8 * ch + 1]);
+    unpack_half2<HK>(t.y, ln[8 * ch + 2], ln[8 * ch + 3]);
+    unpack_half2<HK>(t.z, ln[8 * ch + 4], ln[8 * ch + 5]);
+    unpack_half2<HK>(t.w, ln[8 * ch + 6], ln[8 * ch + 7]);
+  }
+#pragma unroll
+  for (int i = 0; i < 17; ++i) l0[i] = ln[i];
+  l1[0] = ln[17]; l1[1] = ln[18]; l1[10] = ln[19]; l1[11] = ln[20]; l1[12] = ln[21];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) l1[2 + t] = (l0[2 * t] + l0[2 * t + 1]) * 0.5f;
+  l2[0] = ln[22]; l2[1] = ln[23]; l2[8] = ln[24]; l2[9] = ln[25]; l2[10] = ln[26];
+#pragma unroll
+  for (int t = 0; t < 6; ++t) l2[2 + t] = (l1[2 * t] + l1[2 * t + 1]) * 0.5f;
+  l3[0] = ln[27]; l3[1] = ln[28]; l3[7] = ln[29]; l3[8] = ln[30]; l3[9] = ln[31];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) l3[2 + t] = (l2[2 * t] + l2[2 * t + 1]) * 0.5f;
+}
+
 // The 4 x 9 taps at x from the window entries (which are consumed): put(channel, value).
 template <class Put>
 __device__ __forceinline__ void blend_windows(float (&l0)[17], float (&l1)[13], float (&l2)[11], float (&l3)[10], float x,
@@ -330,7 +359,8 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 #ifndef SA_LOOKUP_REGS_VEC
 #define SA_LOOKUP_REGS_VEC 48
 #endif
-template <int NV, int TILE, int OTF, int FV, bool TMA>
+// H0 = storage of volume 0's packed array: 0 fp32 lines (128 B), 1 / 2 fp16 / bf16 lines (64 B, half the staging copies)
+template <int NV, int TILE, int OTF, int FV, bool TMA, int H0>
 __global__ void __maxnreg__(TMA ? SA_LOOKUP_REGS_TMA : SA_LOOKUP_REGS_VEC) lookup_packed_kernel(const PLookupArgs a, const __grid_constant__ CUtensorMap map_o0,
                                                      const __grid_constant__ CUtensorMap map_o1) {
   static_assert(OTF < 0 || FV < 0, "one special mono form at a time");
@@ -429,6 +459,14 @@ __global__ void __maxnreg__(TMA ? SA_LOOKUP_REGS_TMA : SA_LOOKUP_REGS_VEC) looku
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         if (v == OTF || v == FV) continue;
+        if (H0 != 0 && v == 0) {
+          // 16-bit lines: four chunks; the line index counts 16-byte chunks of a 128-byte line - halve it
+          if (ch < 4) {
+            float* dst = buf + pm * 32 + ((((pm & 1) << 2) | (ch ^ ((pm >> 1) & 3))) << 2);
+            cp_async16_zfill(dst, p0 + ((line != ~0u ? line : 0u) >> 1) + ch, ok);
+          }
+          continue;
+        }
         float* dst = buf + (v * TILE + pm) * 32 + ((ch ^ (pm & 7)) << 2);
         cp_async16_zfill(dst, (v ? p1 : p0) + idx, ok);
       }
@@ -531,7 +569,10 @@ __global__ void __maxnreg__(TMA ? SA_LOOKUP_REGS_TMA : SA_LOOKUP_REGS_VEC) looku
       }
     }
   } else {
-    line_levels(buf + tid * 32, p, l0, l1, l2, l3);  // unit index == tid
+    if (H0 != 0 && v == 0)
+      line_levels_half<H0 ? H0 : 1>(buf + tid * 32, p, l0, l1, l2, l3);
+    else
+      line_levels(buf + tid * 32, p, l0, l1, l2, l3);  // unit index == tid
   }
   __syncthreads();  // staging is dead: `buf` becomes the [channel][pixel] output tile
 
@@ -609,12 +650,12 @@ static int output_map(CUtensorMap* m, const float* out, int B, int HW, int tile)
   return 0;
 }
 
-template <int NV, int TILE, int OTF, int FV, bool TMA>
+template <int NV, int TILE, int OTF, int FV, bool TMA, int H0>
 static int launch_packed_tt(PLookupArgs a, int B, cudaStream_t st) {
   constexpr int NC = 36, SP = TMA ? TILE : TILE + 4;
   constexpr int buf_floats = (NV * TILE * 32 > NV * NC * SP) ? NV * TILE * 32 : NV * NC * SP;
   const size_t smem = (size_t)(buf_floats + (FV >= 0 ? 6 : 2) * TILE) * sizeof(float)  /* s_x, s_line [, float4 s_n] */;
-  auto kern = lookup_packed_kernel<NV, TILE, OTF, FV, TMA>;
+  auto kern = lookup_packed_kernel<NV, TILE, OTF, FV, TMA, H0>;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) SA_FAIL((int)e, "sa_lookup_packed: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -639,15 +680,15 @@ static int launch_packed_tt(PLookupArgs a, int B, cudaStream_t st) {
 // 23.8 with the transposed 128-bit stores - it is bound by L1 / shared-memory wavefronts).  Two packed volumes: the
 // 128-bit stores (23.2 against 24.4 us with TMA stores - that form is DRAM-bound and its streaming `no_allocate`
 // stores disturb the line reads less).  SA_B200_LOOKUP_TMA=0/1 overrides.
-template <int NV, int TILE, int OTF, int FV>
+template <int NV, int TILE, int OTF, int FV, int H0>
 static int launch_packed_t(const PLookupArgs& a, int B, cudaStream_t st) {
   static const int env = getenv("SA_B200_LOOKUP_TMA") ? atoi(getenv("SA_B200_LOOKUP_TMA")) : -1;
   const bool want = env >= 0 ? env != 0 : (FV >= 0);
-  if (want && (a.HW & 3) == 0 && encode_fn() != nullptr) return launch_packed_tt<NV, TILE, OTF, FV, true>(a, B, st);
-  return launch_packed_tt<NV, TILE, OTF, FV, false>(a, B, st);
+  if (want && (a.HW & 3) == 0 && encode_fn() != nullptr) return launch_packed_tt<NV, TILE, OTF, FV, true, H0>(a, B, st);
+  return launch_packed_tt<NV, TILE, OTF, FV, false, H0>(a, B, st);
 }
 
-template <int NV, int OTF, int FV = -1>
+template <int NV, int OTF, int FV = -1, int H0 = 0>
 static int launch_packed(PLookupArgs a, int B, cudaStream_t st) {
   // L2 prefetch distance in CTAs (0 = off); SA_B200_LOOKUP_PF overrides
   static const int pf = getenv("SA_B200_LOOKUP_PF") ? atoi(getenv("SA_B200_LOOKUP_PF")) : 0;
@@ -656,9 +697,13 @@ static int launch_packed(PLookupArgs a, int B, cudaStream_t st) {
   static const int tile = getenv("SA_B200_LOOKUP_TILE") ? atoi(getenv("SA_B200_LOOKUP_TILE")) : (FV >= 0 ? 32 : 64);
   // pixels per CTA: 64 measured best at c2 (23.2 us per dual lookup; 128: 24.2, 32: 23.5) - smaller CTAs
   // shorten the tail of the last wave and raise the number of lines in flight per SM
-  if (tile == 32) return launch_packed_t<NV, 32, OTF, FV>(a, B, st);
-  if (tile == 128) return launch_packed_t<NV, 128, OTF, FV>(a, B, st);
-  return launch_packed_t<NV, 64, OTF, FV>(a, B, st);
+  if (H0 != 0) {   // 16-bit storage: 32 or 64 pixels per CTA only (fewer instantiations)
+    if (tile == 32) return launch_packed_t<NV, 32, OTF, FV, H0>(a, B, st);
+    return launch_packed_t<NV, 64, OTF, FV, H0>(a, B, st);
+  }
+  if (tile == 32) return launch_packed_t<NV, 32, OTF, FV, H0>(a, B, st);
+  if (tile == 128) return launch_packed_t<NV, 128, OTF, FV, H0>(a, B, st);
+  return launch_packed_t<NV, 64, OTF, FV, H0>(a, B, st);
 }
 
 }  // namespace sa
@@ -789,4 +834,35 @@ extern "C" int sa_lookup_packed_factored(const float* packed_a, const float* pac
   }
   a.packed[0] = packed_normals_r; a.out[0] = out_mono;
   return launch_packed<1, -1, 0>(a, B, (cudaStream_t)stream);
+}
+
+extern "C" int sa_lookup_packed_half(const void* packed_h_a, int half_kind, int mode_b, const float* packed_b,
+                                     const float* normals_l, float divisor, float post_scale, int W3, const float* coords,
+                                     int64_t coords_bstride, float* out_a, float* out_b, int B, int H, int W, void* stream) {
+  using namespace sa;
+  SA_REQUIRE(packed_h_a && coords && out_a, SA_E_INVALID, "sa_lookup_packed_half: null pointer");
+  SA_REQUIRE(half_kind == 1 || half_kind == 2, SA_E_INVALID, "sa_lookup_packed_half: half_kind must be 1 (fp16) or 2 (bf16)");
+  SA_REQUIRE(mode_b >= 0 && mode_b <= 2, SA_E_INVALID, "sa_lookup_packed_half: mode_b must be 0 (none), 1 (packed fp32) or 2 (factored)");
+  SA_REQUIRE((mode_b == 0) == (out_b == nullptr) && (mode_b == 0 || packed_b) && (mode_b != 2 || (normals_l && divisor != 0.f)),
+             SA_E_INVALID, "sa_lookup_packed_half: second volume arguments do not match mode_b");
+  SA_REQUIRE(B > 0 && H > 0 && W > 0 && B <= 65535 && (long long)H * W < (1ll << 31), SA_E_INVALID, "sa_lookup_packed_half: bad sizes");
+  SA_REQUIRE(W3 >= 8 && W3 % 8 == 0, SA_E_UNSUPPORTED, "sa_lookup_packed_half: W3 must be a multiple of 8");
+  SA_REQUIRE((long long)B * H * W * packed_blocks(W3) < (1ll << 29), SA_E_UNSUPPORTED,
+             "sa_lookup_packed_half: packed array of 64 GB or more (32-bit chunk indices)");
+  SA_REQUIRE(aligned16(packed_h_a) && aligned16(out_a) && (!packed_b || aligned16(packed_b)) && (!out_b || aligned16(out_b)),
+             SA_E_ALIGN, "sa_lookup_packed_half: pointers must be 16-byte aligned");
+  (void)num_sms();
+  PLookupArgs a = {};
+  a.packed[0] = reinterpret_cast<const float*>(packed_h_a); a.packed[1] = packed_b;
+  a.out[0] = out_a; a.out[1] = out_b;
+  a.coords = coords; a.coords_bstride = coords_bstride;
+  a.HW = H * W; a.W3 = W3; a.nblk = packed_blocks(W3);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode_b == 2) {
+    a.nl = normals_l; a.H = H; a.Wimg = W;
+    a.divisor = kernel_divisor(divisor); a.inv_divisor = kernel_inv_divisor(divisor); a.post_scale = post_scale;
+    return half_kind == 1 ? launch_packed<2, -1, 1, 1>(a, B, st) : launch_packed<2, -1, 1, 2>(a, B, st);
+  }
+  if (mode_b == 1) return half_kind == 1 ? launch_packed<2, -1, -1, 1>(a, B, st) : launch_packed<2, -1, -1, 2>(a, B, st);
+  return half_kind == 1 ? launch_packed<1, -1, -1, 1>(a, B, st) : launch_packed<1, -1, -1, 2>(a, B, st);
 }

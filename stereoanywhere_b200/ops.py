@@ -322,6 +322,82 @@ def _corr_pack(fmap_l: torch.Tensor, fmap_r: torch.Tensor, trunc_disp: Optional[
     return packed
 
 
+HALF_KINDS = {"fp16": (1, torch.float16), "bf16": (2, torch.bfloat16)}
+
+
+def _corr_pack_half(fmap_l: torch.Tensor, fmap_r: torch.Tensor, trunc_disp: Optional[torch.Tensor],
+                    trunc_conf: Optional[torch.Tensor], trunc_gain: float, kind: int) -> torch.Tensor:
+    """`_corr_pack` with the packed pyramid stored in 16 bits (kind 1 = fp16, 2 = bf16): [rows, (W3/8 + 9) * 32] of
+    that dtype (csrc/corr_pack_tcgen05.cu, sa_corr_pack_tf32_half)."""
+    _cuda_f32(fmap_l, "fmap_l")
+    _cuda_f32(fmap_r, "fmap_r")
+    _req(kind in (1, 2), "half storage kind must be 1 (fp16) or 2 (bf16)")
+    b, c, h, w2 = fmap_l.shape
+    _req(fmap_r.shape[:3] == (b, c, h), "left/right feature maps must share B, C, H")
+    w3 = fmap_r.shape[3]
+    _req(corr_packable(c, w2, w3), "corr_pack needs C % 32 == 0, W2 % 4 == 0, W3 % 8 == 0")
+    fmap_l, fmap_r = fmap_l.contiguous(), fmap_r.contiguous()
+    rows = b * h * w2
+    packed = torch.empty((rows, packed_row_floats(w3)), dtype=torch.float16 if kind == 1 else torch.bfloat16,
+                         device=fmap_l.device)
+    td = tc = None
+    if trunc_disp is not None:
+        _cuda_f32(trunc_disp, "trunc_disp")
+        _cuda_f32(trunc_conf, "trunc_conf")
+        trunc_disp, trunc_conf = trunc_disp.contiguous(), trunc_conf.contiguous()
+        _req(trunc_disp.numel() == rows and trunc_conf.numel() == rows,
+             "truncation maps must be [B,1,H,W2] matching the left feature map")
+        td, tc = trunc_disp.data_ptr(), trunc_conf.data_ptr()
+    lib = _lib.load()
+    with _on(fmap_l.device):
+        rc = lib.sa_corr_pack_tf32_half(fmap_l.data_ptr(), fmap_r.data_ptr(), b, c, h, w2, w3, _divisor(c), 1.0, td, tc,
+                                        float(trunc_gain), kind, packed.data_ptr(), _stream_ptr(packed))
+    _lib.check(rc, "sa_corr_pack_tf32_half")
+    return packed
+
+
+def _lookup_half(packed_h: torch.Tensor, kind: int, mode_b: int, packed_b: Optional[torch.Tensor],
+                 normals_l: Optional[torch.Tensor], post_scale: float, w3: int, coords: torch.Tensor):
+    """Lookup with volume A in 16-bit storage; mode_b 0 = alone, 1 = with an fp32 packed volume, 2 = with the
+    factored mono volume (packed_b = packed right normals).  Returns (out_a, out_b or None)."""
+    coords, b, h, w = _coords_view(coords)
+    _req(packed_h.is_cuda and packed_h.dtype == (torch.float16 if kind == 1 else torch.bfloat16),
+         "packed_h must be a CUDA tensor of the storage dtype")
+    _req(packed_h.shape == (b * h * w, packed_row_floats(w3)) and packed_h.is_contiguous(),
+         "coords do not match the volume this block was built from")
+    out_a = torch.empty((b, 36, h, w), dtype=torch.float32, device=coords.device)
+    out_b = torch.empty_like(out_a) if mode_b else None
+    pb = nl = None
+    divisor = 1.0
+    if mode_b == 1:
+        _cuda_f32(packed_b, "packed pyramid")
+        _req(packed_b.shape == (b * h * w, packed_row_floats(w3)), "lookup of two volumes needs identical geometry")
+        pb = packed_b.data_ptr()
+    elif mode_b == 2:
+        _cuda_f32(packed_b, "packed right normals")
+        _cuda_f32(normals_l, "normals_l")
+        _req(normals_l.shape == (b, 3, h, w), "normals_l must be [B,3,H,W] matching coords")
+        _req(packed_b.dim() == 2 and packed_b.shape == (b * 3 * h, packed_row_floats(w3)) and packed_b.is_contiguous(),
+             "packed right normals must be [B*3*H, row floats]")
+        normals_l = normals_l.contiguous()
+        pb, nl, divisor = packed_b.data_ptr(), normals_l.data_ptr(), _divisor(3)
+    lib = _lib.load()
+    with _on(coords.device):
+        rc = lib.sa_lookup_packed_half(packed_h.data_ptr(), kind, mode_b, pb, nl, divisor, float(post_scale), w3,
+                                       coords.data_ptr(), coords.stride(0), out_a.data_ptr(),
+                                       out_b.data_ptr() if out_b is not None else None, b, h, w, _stream_ptr(coords))
+    _lib.check(rc, "sa_lookup_packed_half")
+    return out_a, out_b
+
+
+def _lookup_half1(packed_h, kind, w3, coords):
+    return _lookup_half(packed_h, kind, 0, None, None, 1.0, w3, coords)[0]
+
+
+def _lookup_half2(packed_h, kind, mode_b, packed_b, normals_l, post_scale, w3, coords):
+    return _lookup_half(packed_h, kind, mode_b, packed_b, normals_l, post_scale, w3, coords)
+
+
 def corr_packable(c: int, w2: int, w3: int) -> bool:
     return c % 32 == 0 and c >= 32 and w2 % 4 == 0 and w3 >= 8 and w3 % 8 == 0
 
@@ -657,6 +733,9 @@ _LIBDEF.define("lookup2(Tensor[] levels_a, Tensor[] levels_b, int[] widths, Tens
 _LIBDEF.define("pack_pyramid(Tensor vol_rows, Tensor? trunc_disp, Tensor? trunc_conf, float trunc_gain) -> Tensor")
 _LIBDEF.define("pack_pyramid_normals(Tensor normals_l, Tensor normals_r, float post_scale) -> Tensor")
 _LIBDEF.define("corr_pack(Tensor fmap_l, Tensor fmap_r, Tensor? trunc_disp, Tensor? trunc_conf, float trunc_gain) -> Tensor")
+_LIBDEF.define("corr_pack_half(Tensor fmap_l, Tensor fmap_r, Tensor? trunc_disp, Tensor? trunc_conf, float trunc_gain, int kind) -> Tensor")
+_LIBDEF.define("lookup_half(Tensor packed_h, int kind, int w3, Tensor coords) -> Tensor")
+_LIBDEF.define("lookup_half2(Tensor packed_h, int kind, int mode_b, Tensor packed_b, Tensor? normals_l, float post_scale, int w3, Tensor coords) -> (Tensor, Tensor)")
 _LIBDEF.define("volume_softargmax(Tensor vol) -> (Tensor, Tensor)")
 _LIBDEF.define("volume_entropy_conf(Tensor vol) -> (Tensor, Tensor)")
 _LIBDEF.define("lookup_normals(Tensor normals_l, Tensor normals_r, float post_scale, Tensor coords) -> Tensor")
@@ -678,6 +757,9 @@ _LIBDEF.impl("lookup2", _lookup2, "CUDA")
 _LIBDEF.impl("pack_pyramid", _pack_pyramid, "CUDA")
 _LIBDEF.impl("pack_pyramid_normals", _pack_pyramid_normals, "CUDA")
 _LIBDEF.impl("corr_pack", _corr_pack, "CUDA")
+_LIBDEF.impl("corr_pack_half", _corr_pack_half, "CUDA")
+_LIBDEF.impl("lookup_half", _lookup_half1, "CUDA")
+_LIBDEF.impl("lookup_half2", _lookup_half2, "CUDA")
 _LIBDEF.impl("volume_softargmax", _volume_softargmax, "CUDA")
 _LIBDEF.impl("volume_entropy_conf", _volume_entropy_conf, "CUDA")
 _LIBDEF.impl("lookup_normals", _lookup_normals1, "CUDA")
@@ -692,5 +774,5 @@ _LIBDEF.impl("truncate", _truncate, "CUDA")
 _LIBDEF.impl("masked_volume", _masked_volume, "CUDA")
 _LIBDEF.impl("corrupt", _corrupt, "CUDA")
 
-OP_NAMES = ["corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "corr_pack", "lookup_normals", "lookup_packed_normals2", "lookup_factored", "lookup_packed_factored2", "volume_softargmax", "volume_entropy_conf", "lookup_packed", "lookup_packed2", "lookup_packed_conv", "lookup_factored_conv",
+OP_NAMES = ["corr_pack_half", "lookup_half", "lookup_half2", "corr_volume", "pyramid", "lookup", "lookup2", "pack_pyramid", "pack_pyramid_normals", "corr_pack", "lookup_normals", "lookup_packed_normals2", "lookup_factored", "lookup_packed_factored2", "volume_softargmax", "volume_entropy_conf", "lookup_packed", "lookup_packed2", "lookup_packed_conv", "lookup_factored_conv",
             "truncate", "masked_volume", "corrupt"]

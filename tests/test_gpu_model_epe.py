@@ -220,6 +220,26 @@ def test_real_model_under_mixed_precision_autocast(variant):
     assert epe < GATE_PX, f"EPE {epe} px exceeds the {GATE_PX} px gate"
 
 
+@pytest.mark.parametrize("storage", ["fp16", "bf16"])
+def test_real_model_epe_with_16_bit_storage(storage):
+    """The opt-in 16-bit storage of the stereo block's packed pyramid (`CorrBlockB200.storage`) under the same gate:
+    the benchmarked wiring (fused, raw mono volume) inside the real model, 32 iterations."""
+    margs = {"use_aggregate_mono_vol": False}
+    sa_mod, model, B, integration = _setup(margs)
+    inputs = _inputs(384, 512)
+    d_ref = _forward(model, inputs)
+    old, B.storage = B.storage, storage
+    try:
+        integration.install(sa_mod, fused=True)
+        d_b200 = _forward(model, inputs)
+    finally:
+        B.storage = old
+        integration.uninstall(sa_mod)
+    epe = float((d_b200 - d_ref).abs().mean())
+    print(f"[storage {storage}] EPE {epe:.2e} px (max {float((d_b200 - d_ref).abs().max()):.2e})")
+    assert epe < GATE_PX, f"EPE {epe} px exceeds the {GATE_PX} px gate"
+
+
 def test_half_precision_volume_and_maps():
     """Under the reference's --mixed_precision autocast (test.py:63,189) the hourglass / classifier volumes and the
     truncation maps arrive in fp16; `CorrBlock1D` takes any dtype (bilinear_sampler casts, utils/utils.py:19-35)."""

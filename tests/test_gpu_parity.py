@@ -864,3 +864,69 @@ def test_more_than_2_31_packed_floats(sa):
         m1 = B.from_normals(nl[sl].contiguous(), nr[sl].contiguous())
         s1, mm1 = B.lookup_pair(f1, m1, coords[sl].contiguous())
         assert torch.equal(s_all[sl], s1) and torch.equal(m_all[sl], mm1), i
+
+
+# ------------------------------------------------------------------------------------------ 16-bit storage of the packed pyramid
+
+@pytest.mark.parametrize("storage", ["fp16", "bf16"])
+@pytest.mark.parametrize("b,c,h,w2,w3", [(1, 64, 3, 312, 312), (2, 32, 2, 40, 72), (1, 256, 2, 168, 168), (1, 32, 1, 8, 8),
+                                         (1, 96, 2, 132, 264)])
+def test_half_storage_is_the_fp32_pyramid_rounded(sa, storage, b, c, h, w2, w3):
+    """`from_features(..., storage=)` (sa_corr_pack_tf32_half): the 16-bit packed array is the fp32 one rounded to
+    nearest, element for element; a lookup from it equals, bit for bit, the fp32 lookup of the widened array; dual
+    lookups with a factored / an fp32-packed partner equal the single lookups."""
+    from stereoanywhere_b200 import ops
+
+    kind, dt = ops.HALF_KINDS[storage]
+    B = sa.CorrBlockB200
+    gen = torch.Generator(device=DEV).manual_seed(w2 + w3 + c)
+    fl = torch.randn(b, c, h, w2, device=DEV, generator=gen)
+    fr = torch.randn(b, c, h, w3, device=DEV, generator=gen)
+    tdisp = torch.rand(b, 1, h, w2, device=DEV, generator=gen) * (w3 / 4)
+    tconf = torch.rand(b, 1, h, w2, device=DEV, generator=gen)
+    x = torch.arange(w2, device=DEV, dtype=torch.float32).view(1, 1, 1, w2).expand(b, 1, h, w2)
+    coords = torch.cat([x - torch.rand(b, 1, h, w2, device=DEV, generator=gen) * (w3 / 3) + 2, torch.zeros(b, 1, h, w2, device=DEV)], 1)
+    for trunc in (None, (tdisp, tconf, 0.9)):
+        full = B.from_features(fl, fr, truncate=trunc)
+        half = B.from_features(fl, fr, truncate=trunc, storage=storage)
+        assert half._packed is None and half._packed_h.dtype == dt
+        assert torch.equal(half._packed_h, full._packed.to(dt))
+        widened = torch.ops.sa_b200.lookup_packed(half._packed_h.float(), w3, coords)
+        got = half(coords)
+        assert torch.equal(got, widened)
+        tol = 1e-3 if storage == "fp16" else 1e-2
+        assert normwise(got, full(coords)) < tol
+        if w2 == w3:   # partners need the same geometry
+            nl = torch.nn.functional.normalize(torch.randn(b, 3, h, w2, device=DEV, generator=gen), dim=1)
+            nr = torch.nn.functional.normalize(torch.randn(b, 3, h, w3, device=DEV, generator=gen), dim=1)
+            for mode in ("factored", "packed"):
+                old, B.mono_mode = B.mono_mode, mode
+                try:
+                    mono = B.from_normals(nl, nr)
+                finally:
+                    B.mono_mode = old
+                s_, m_ = B.lookup_pair(half, mono, coords)
+                assert torch.equal(s_, got) and torch.equal(m_, mono(coords)), mode
+            dense = B(torch.randn(b, h, w2, 1, w3, device=DEV, generator=gen))
+            s_, m_ = B.lookup_pair(half, dense, coords)
+            assert torch.equal(s_, got) and torch.equal(m_, dense(coords))
+        # the reference attributes still work (formed in fp32 from the feature maps)
+        assert torch.equal(half.fullcorr, full.fullcorr)
+
+
+def test_half_storage_vs_float64_at_kitti_width(sa):
+    """TF32 product + fp16 storage against float64 on sampled pixels at W = 312, C = 256: inside the 1e-3 of the TF32
+    class; bf16 inside 1e-2."""
+    b, c, h, w = 2, 256, 8, 312
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    fl = torch.randn(b, c, h, w, device=DEV, generator=gen)
+    fr = torch.randn(b, c, h, w, device=DEV, generator=gen)
+    x = torch.arange(w, device=DEV, dtype=torch.float32).view(1, 1, 1, w).expand(b, 1, h, w)
+    coords = torch.cat([x - torch.rand(b, 1, h, w, device=DEV, generator=gen) * 78, torch.zeros(b, 1, h, w, device=DEV)], 1)
+    vol64 = torch.einsum("bchw,bchv->bhwv", fl.double(), fr.double()) / 16.0
+    want = sampled_closed_lookup(vol64.view(b * h * w, w), coords[:, 0].reshape(-1))
+    for storage, tol in (("fp32", 1e-3), ("fp16", 1e-3), ("bf16", 1e-2)):
+        got = sa.CorrBlockB200.from_features(fl, fr, storage=storage)(coords).permute(0, 2, 3, 1).reshape(b * h * w, 36).double()
+        err = float((got - want).abs().max() / vol64.abs().max())
+        print(f"storage {storage}: normwise lookup error {err:.2e}")
+        assert err < tol, (storage, err)

@@ -7,6 +7,7 @@ import bench
 import stereoanywhere_b200 as sa
 B = sa.CorrBlockB200
 b, c, h, w = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else bench.DEFAULT_WORKLOAD]
+storage = sys.argv[2] if len(sys.argv) > 2 else "fp32"
 dev = torch.device("cuda:0")
 _, d = bench.make_inputs(b, c, h, w, dev, seed=0)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -24,4 +25,4 @@ def timeit(fn, reps=10):
     return ts[len(ts) // 2]
 for name, t in (("no truncation", None), ("random disparities (bench)", (d["tdisp"], d["tconf"], 0.9)),
                 ("smooth disparities", (smooth, d["tconf"], 0.9))):
-    print(f"{name:32s} {timeit(lambda: B.from_features(d['fl'], d['fr'], truncate=t)):7.1f} us")
+    print(f"{storage} {name:32s} {timeit(lambda: B.from_features(d['fl'], d['fr'], truncate=t, storage=storage)):7.1f} us")

@@ -216,7 +216,6 @@ struct PLookupArgs {
   float divisor, inv_divisor, post_scale;
   // factored mono volume (FV >= 0): packed[FV] holds the packed pyramid of the RIGHT NORMAL MAP's rows,
   // [(b*3 + c)*H + h][nblk][32]; nl / H / Wimg / divisor / inv_divisor / post_scale as above
-  int pf_dist;  // > 0: the idle prologue warp(s) pull the lines of the CTA `pf_dist` launches ahead into L2
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -415,27 +414,6 @@ __global__ void __maxnreg__(TMA ? SA_LOOKUP_REGS_TMA : SA_LOOKUP_REGS_VEC) looku
       for (unsigned w = a.Wimg; w <= t; w += a.Wimg) ++hh;
       const unsigned off = blk >= 0 ? (((b * 3u) * a.H + hh) * (unsigned)a.nblk + (unsigned)blk) * 8u : 0u;
       s_n[tid] = make_float4(n0 * k, n1 * k, n2 * k, __uint_as_float(off));
-    }
-  }
-  else if (NV == 2 && a.pf_dist > 0) {
-    // Optional (SA_B200_LOOKUP_PF, off by default: measured neutral, profiles/r2/lookup_l2_prefetch_sweep.txt): the
-    // second half of the CTA, idle in the prologue, pulls the lines of the CTA `pf_dist` launches ahead into L2.
-    const int t = tid - TILE;
-    const long long lin = (long long)blockIdx.y * gridDim.x + blockIdx.x + a.pf_dist;
-    if (lin < (long long)gridDim.x * gridDim.y) {
-      const int pb = (int)(lin / gridDim.x);
-      const int phw = (int)(lin - (long long)pb * gridDim.x) * TILE + t;
-      if (phw < a.HW) {
-        const float x = __ldg(a.coords + (long long)pb * a.coords_bstride + phw);
-        const float fl = fminf(fmaxf(floorf(x), -1.0e6f), 1.0e6f);
-        const int q = ((int)fl >> 3) - kQMin;
-        if (q >= 0 && q < a.nblk) {
-          const long long off = (((long long)pb * a.HW + phw) * a.nblk + q) * 32;
-#pragma unroll
-          for (int v = 0; v < NV; ++v)
-            if (v != OTF && v != FV) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.packed[v] + off));
-        }
-      }
     }
   }
   __syncthreads();
@@ -690,9 +668,8 @@ static int launch_packed_t(const PLookupArgs& a, int B, cudaStream_t st) {
 
 template <int NV, int OTF, int FV = -1, int H0 = 0>
 static int launch_packed(PLookupArgs a, int B, cudaStream_t st) {
-  // L2 prefetch distance in CTAs (0 = off); SA_B200_LOOKUP_PF overrides
-  static const int pf = getenv("SA_B200_LOOKUP_PF") ? atoi(getenv("SA_B200_LOOKUP_PF")) : 0;
-  a.pf_dist = pf;
+  // (an L2 prefetch of the lines of the CTA k launches ahead, issued by the warp that idles in the prologue, was
+  // measured neutral at every distance - profiles/r2/lookup_l2_prefetch_sweep.txt - and removed)
   // (factored mono volume: 32 - 23.5 us against 24.4 at 64 and 27.3 at 128; its staging is latency-bound)
   static const int tile = getenv("SA_B200_LOOKUP_TILE") ? atoi(getenv("SA_B200_LOOKUP_TILE")) : (FV >= 0 ? 32 : 64);
   // pixels per CTA: 64 measured best at c2 (23.2 us per dual lookup; 128: 24.2, 32: 23.5) - smaller CTAs

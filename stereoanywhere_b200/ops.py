@@ -8,7 +8,6 @@ at first use.
 from __future__ import annotations
 
 import ctypes as C
-import math
 import os
 from typing import List, Optional, Sequence, Tuple
 

@@ -240,6 +240,42 @@ def test_real_model_epe_with_16_bit_storage(storage):
     assert epe < GATE_PX, f"EPE {epe} px exceeds the {GATE_PX} px gate"
 
 
+def test_real_model_tiled_full_resolution_middlebury():
+    """BASELINE config 4 end to end with the real model: the reference's own `TileWrapper` (mapreduce_v2/tile_wrapper.py,
+    `middlebury` preset 672 x 1120, overlap 112: 12 tiles, the reference block, serial accumulate) against
+    `tiling.tiled_inference_b200` (10 distinct tiles weighted by multiplicity, the B200 block in the fused wiring, slot
+    stitch) on a 1984 x 2880 pair, 32 iterations per tile."""
+    from stereoanywhere_b200 import tiling
+
+    sa_mod, model, B, integration = _setup({"use_aggregate_mono_vol": False})
+    T = ref_shim.import_reference_tiles()
+    h, w = 1984, 2880
+    left, right, ml, mr = _inputs(h, w)
+    th, tw, ov = tiling.PRESETS["middlebury"]
+    wrap = T.TileWrapper(model, tile_width=tw, tile_height=th, overlap=ov)
+    random.seed(0)
+    with torch.no_grad():
+        d_ref = wrap(left, right, ml, mr, iters=32, test_mode=True)
+    torch.cuda.synchronize()
+
+    def run_model(l_, r_, ml_, mr_):
+        return model(l_, r_, ml_, mr_, iters=32, test_mode=True)
+
+    try:
+        integration.install(sa_mod, fused=True)
+        random.seed(0)
+        with torch.no_grad():
+            d_b200 = tiling.tiled_inference_b200(run_model, left, right, ml, mr, th, tw, ov)
+    finally:
+        integration.uninstall(sa_mod)
+    torch.cuda.synchronize()
+    assert d_b200.shape == d_ref.shape == (1, 1, h, w)
+    epe = float((d_b200 - d_ref).abs().mean())
+    print(f"[tiled 1984x2880, middlebury preset] EPE {epe:.2e} px (max {float((d_b200 - d_ref).abs().max()):.2e}); "
+          f"mean |disp| {float(d_ref.abs().mean()):.3f} px")
+    assert epe < GATE_PX, f"EPE {epe} px exceeds the {GATE_PX} px gate"
+
+
 def test_half_precision_volume_and_maps():
     """Under the reference's --mixed_precision autocast (test.py:63,189) the hourglass / classifier volumes and the
     truncation maps arrive in fp16; `CorrBlock1D` takes any dtype (bilinear_sampler casts, utils/utils.py:19-35)."""

@@ -350,8 +350,9 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 // line, one float4 of the output): a packed array of up to 64 GB.  The first version formed every address in 64 bits
 // per thread - 370 of its 950 SASS instructions were integer address arithmetic in a kernel that is issue-bound
 // (DESIGN 7c); see profiles/r2 for the before / after instruction mix.
-// 48 registers: 21 CTAs of 64 threads per SM instead of 18 (the compiler would take 55; the factored form spills one
-// value) - the kernel is latency-bound, resident warps are what hides its three dependent phases.
+// Register budgets (measured, profiles/r2/lookup_variants_sweep.txt): 56 for the TMA-store form, 48 for the 128-bit-store
+// form (21 CTAs of 64 threads per SM instead of 18); the on-the-fly mono form forms 80 values per thread and keeps
+// its free budget.
 #ifndef SA_LOOKUP_REGS_TMA
 #define SA_LOOKUP_REGS_TMA 56
 #endif
@@ -360,7 +361,7 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
 #endif
 // H0 = storage of volume 0's packed array: 0 fp32 lines (128 B), 1 / 2 fp16 / bf16 lines (64 B, half the staging copies)
 template <int NV, int TILE, int OTF, int FV, bool TMA, int H0>
-__global__ void __maxnreg__(TMA ? SA_LOOKUP_REGS_TMA : SA_LOOKUP_REGS_VEC) lookup_packed_kernel(const PLookupArgs a, const __grid_constant__ CUtensorMap map_o0,
+__global__ void __maxnreg__(OTF >= 0 ? 128 : (TMA ? SA_LOOKUP_REGS_TMA : SA_LOOKUP_REGS_VEC)) lookup_packed_kernel(const PLookupArgs a, const __grid_constant__ CUtensorMap map_o0,
                                                      const __grid_constant__ CUtensorMap map_o1) {
   static_assert(OTF < 0 || FV < 0, "one special mono form at a time");
   constexpr int THREADS = NV * TILE;

@@ -10,9 +10,10 @@ reference model by adding one branch at stereoanywhere.py:128-133 (see INTEGRATI
 
 All arithmetic runs in the sm_100a kernels behind `torch.ops.sa_b200.*`; there is no CPU path.
 Training: a volume / feature map that requires grad makes `corr()`, the constructor and
-`__call__` autograd nodes whose backward runs `sa_lookup_backward` / `sa_pyramid_backward` (and two library
-GEMMs for `corr()`); coords are detached before every lookup in the reference (stereoanywhere.py:268) and must
-not require grad here.
+`__call__` autograd nodes whose backward runs `sa_lookup_backward` / `sa_pyramid_backward` / `sa_corr_backward_tf32`
+(both products of the adjoint of `corr()` on the tensor cores; the C = 3 mono volume and "fp32" precision take two
+library GEMMs); coords are detached before every lookup in the reference (stereoanywhere.py:268) and must not
+require grad here.
 
 Beyond the strict protocol (used when the caller's wiring allows, reference call sites in
 brackets):
@@ -227,7 +228,7 @@ class CorrBlockB200:
     #: left normal while staging: no mono pack pass (241 us) and half the lookup's DRAM reads; within fp32 rounding
     #: (<= 1e-6 abs) of the packed mode.  "packed" writes the packed pyramid of the volume itself, bit-identical to
     #: `cls(cls.mono_corr(nL, nR))`.  "otf" keeps only the normal maps and forms 80 level-0 values per pixel inside
-    #: the lookup kernel - bit-identical to "packed" too, but 44.6 us instead of 23.3 us per dual lookup.
+    #: the lookup kernel - bit-identical to "packed" too, but 48 us instead of 23 us per dual lookup (a memory-saving mode).
     #: SA_B200_MONO overrides the default.
     mono_mode = os.environ.get("SA_B200_MONO", "factored")
 

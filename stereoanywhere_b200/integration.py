@@ -6,7 +6,9 @@
 Two modes:
 
 * `fused=False` - `CorrBlock1D := CorrBlockB200`.  The reference's call sequence runs op for op (`corr()` x 2,
-  `1.73 *`, truncation mask, product, two constructors, 64 lookups); every one of them is a kernel of this package.
+  `1.73 *`, truncation mask, product, two constructors, 64 lookups): `corr()`, the constructors (pyramid) and the
+  lookups are kernels of this package; the `1.73 *`, the truncation mask and its product stay the reference's own
+  PyTorch ops on the dense volume.
 * `fused=True`  - the same calls, but the full-volume intermediates are never formed when nobody reads them.
   `corr()` returns a `LazyVolume` (it remembers the two maps), `truncate_corr_volume_v2(..., conf_th=None)` a
   `LazyTruncation` (it remembers disp / conf / gain); their product, the reshapes of stereoanywhere.py:135-136 /

@@ -9,9 +9,10 @@ The reference forms the inputs of the mono volume and of the truncation mask wit
 `[B,1,H/4,W/4]` maps (stereoanywhere.py:109-114, 138-139, 191): a bilinear 1/4 resize, `estimate_normals`
 (utils/utils.py:73-77), `generate_masks` (:48-54) and the per-sample `weighted_lsq` (:345-384), whose Python loop
 runs two `torch.quantile`s, boolean-mask gathers (a device->host sync each) and a `torch.linalg.lstsq` per
-sample.  These maps are far below a megabyte per pair - there is nothing to win with custom kernels - but at
-batch 64 the syncs serialise the stream in front of the hot path.  The functions here are the same arithmetic as
-batched tensor ops that never leave the stream: plain PyTorch, any device.
+sample.  These maps are far below a megabyte per pair, so the cost is launches and syncs, not bytes: at batch 64 the
+reference's `weighted_lsq` alone issues 5 762 launches and 576 device->host syncs in front of the hot path; the two
+kernels are two launches and no sync (profiles/r2/producers_launches_syncs.txt).  The host mirror is the same arithmetic as batched tensor ops
+that never leave the stream: plain PyTorch, any device.
 
 Parity: `tests/golden/producers.npz` (generated from the reference).  `generate_masks` is bit-exact;
 `weighted_lsq` solves the same 2-parameter weighted least-squares problem through its normal equations in

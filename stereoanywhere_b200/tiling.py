@@ -351,6 +351,10 @@ def tiled_inference_b200(model: Callable[..., torch.Tensor], left: torch.Tensor,
         return tiled_inference(model, left, right, mono_left, mono_right, tile_h, tile_w, overlap, group=group, dst=dst)
     if stitcher is None:
         work = tile_multiplicity(height, width, tile_h, tile_w, overlap)
+        if width % 4 or any(x0 % 4 or (x1 - x0) % 4 for (_y0, _y1, x0, x1), _m in work):
+            # the stitch kernels move float4 columns; odd geometries take the portable stitch (one `reduce`)
+            return tiled_inference(model, left, right, mono_left, mono_right, tile_h, tile_w, overlap, group=group,
+                                   unique=True, dst=dst)
         stitcher = SlotStitcher(1, height, width, work, left.device, group=group, dst=dst)
     stitcher.begin()
     for u in stitcher.my_units():

@@ -117,6 +117,11 @@ def test_stitch_kernels_match_the_reference_tile_wrapper(golden_tiles):
     for _ in range(5):
         again = tiling.tiled_inference_b200(toy, l, r, ml, mr, th, tw, ov, stitcher=st)
         assert torch.equal(again, out)
+    # a geometry the float4 stitch kernels do not cover (218 columns: tiles start at 0, 72, 122) takes the portable
+    # stitch instead of raising
+    odd = tiling.tiled_inference_b200(toy, l[..., :218], r[..., :218], ml[..., :218], mr[..., :218], th, tw, ov)
+    host_odd = tiling.tiled_inference(toy, l[..., :218], r[..., :218], ml[..., :218], mr[..., :218], th, tw, ov, unique=True)
+    assert odd.shape == (1, 1, 150, 218) and torch.equal(odd, host_odd)
 
 
 def test_stitch_error_codes(lib):

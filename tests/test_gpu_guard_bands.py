@@ -288,3 +288,33 @@ def test_the_arena_notices_a_stray_write():
     with pytest.raises(AssertionError, match="wrote outside"):
         ar.check("deliberate overrun")
     assert t.numel() == 10
+
+
+def test_full_size_results_repeat_bit_for_bit(sa):
+    """No sanitizer on the pool for race checks either: at KITTI size (7 488 lookup CTAs, 2 256 stripes, every SM busy) the
+    fused constructor, the dual lookups and the fused lookup + convc1 must return the same bits on every run."""
+    import bench
+
+    B = sa.CorrBlockB200
+    b, c, h, w = bench.WORKLOADS["c2_kitti_375x1242_b8"]
+    _, d = bench.make_inputs(b, c, h, w, torch.device(DEV), seed=0)
+    first = B.from_features(d["fl"], d["fr"], truncate=(d["tdisp"], d["tconf"], 0.9))
+    mono = B.from_normals(d["nl"], d["nr"])
+    for _ in range(3):
+        again = B.from_features(d["fl"], d["fr"], truncate=(d["tdisp"], d["tconf"], 0.9))
+        assert torch.equal(again._packed, first._packed)
+        del again
+    half = B.from_features(d["fl"], d["fr"], truncate=(d["tdisp"], d["tconf"], 0.9), storage="fp16")
+    g = torch.Generator(device=DEV).manual_seed(1)
+    wgt, bias = torch.randn(64, 36, 1, 1, device=DEV, generator=g) * 0.2, torch.randn(64, device=DEV, generator=g)
+    coords = d["coords0"]
+    s0, m0 = B.lookup_pair(first, mono, coords)
+    h0, hm0 = B.lookup_pair(half, mono, coords)
+    c0, cm0 = sa.lookup_pair_convc1(first, mono, coords, wgt, bias)
+    for _ in range(10):
+        s, m = B.lookup_pair(first, mono, coords)
+        assert torch.equal(s, s0) and torch.equal(m, m0)
+        hs, hm = B.lookup_pair(half, mono, coords)
+        assert torch.equal(hs, h0) and torch.equal(hm, hm0)
+        cs, cm = sa.lookup_pair_convc1(first, mono, coords, wgt, bias)
+        assert torch.equal(cs, c0) and torch.equal(cm, cm0)

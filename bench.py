@@ -947,6 +947,7 @@ def run_reference(args):
         t += dt
     value = pairs * args.steps / t
     sample = (f"each step = {pairs} of {b} pairs of {args.workload}, all {ITERS} iterations, {what} on the host cores")
+    on_gpu = reference_on_gpu(args, fn) if kind == "reference" else None
     emit({
         "impl": "reference", "metric": metric_for(args.workload), "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(t / args.steps * 1e3, 2),
@@ -955,7 +956,42 @@ def run_reference(args):
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        **({"reference_on_b200": on_gpu} if on_gpu else {}),
     })
+
+
+def reference_on_gpu(args, fn):
+    """SURVEY 8d's "real bar", reported next to the CPU number of the reference arm: the SAME unmodified reference
+    classes executed by ATen on cuda:0 (device-resident inputs, the whole batch, all 32 iterations, including the
+    reference's per-level `torch.unique` host sync).  None when there is no GPU."""
+    if not torch.cuda.is_available():
+        return None
+    try:
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        b, c, h, w = WORKLOADS[args.workload]
+        _, d = make_inputs(b, c, h, w, dev, seed=0)
+        coords = [d["coords0"] + k * d["delta"] for k in range(ITERS)]
+
+        def step():
+            with torch.no_grad():
+                fn(d["fl"], d["fr"], d["nl"], d["nr"], coords, trunc=(d["tdisp"], d["tconf"], 0.9), radius=RADIUS,
+                   num_levels=LEVELS)
+
+        for _ in range(max(args.warmup, 1)):
+            step()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / args.steps
+        return {"value": round(b / ms * 1e3, 2), "unit": UNIT, "ms_per_step": round(ms, 3), "pairs_per_step": b,
+                "what": "the same unmodified CorrBlock1D / truncate_corr_volume_v2 (oracle/_ref) run by ATen on this B200, "
+                        "device-resident inputs - the reference as a GPU user runs it today"}
+    except Exception as e:  # the CPU number is the arm's result; this is extra information
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
 _RESULT_OUT = None

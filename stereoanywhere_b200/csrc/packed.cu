@@ -565,7 +565,10 @@ __global__ void __maxnreg__(OTF >= 0 ? 128 : (TMA ? SA_LOOKUP_REGS_TMA : SA_LOOK
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (tid < NV) {
-      tma_store_3d(tid ? &map_o1 : &map_o0, buf + tid * NC * SP, (int)hw0, 0, (int)b);
+      // evict_first: the 69 MB a launch writes would otherwise sit dirty in the L2 and push out the packed lines and
+      // right-normal rows that the next iteration reads again (coordinates move by a fraction of a pixel per
+      // iteration) - 22.7 -> 21.1 us per dual lookup at KITTI size (profiles/r2/lookup_l2_policy_sweep.txt)
+      tma_store_3d_hint(tid ? &map_o1 : &map_o0, buf + tid * NC * SP, (int)hw0, 0, (int)b, l2_evict_first_policy());
       tma_commit();
       tma_wait_read<0>();   // the tile must outlive the store's read of it
     }

@@ -607,7 +607,10 @@ def run_gpu(args):
                 # SURVEY 8d counts 612 B/px for the dual lookup (both volumes' windows read from memory); the factored
                 # and on-the-fly forms do not read the mono windows, `achieved` above uses their own smaller figure
                 "survey_8d_definition": {"bytes_per_pixel": s8d, "gbs": round(s8d * p / (lk_launch_ms * 1e-3) / 1e9, 1),
-                                         "frac": round(s8d * p / (lk_launch_ms * 1e-3) / 1e9 / peak, 4)},
+                                         "frac": round(s8d * p / (lk_launch_ms * 1e-3) / 1e9 / peak, 4),
+                                         "note": "informational: SURVEY 8d's per-pixel figure counts mono windows that the "
+                                                 "factored / on-the-fly forms never read, so this can exceed 1; `frac` above "
+                                                 "is on the bytes this kernel's own algorithm needs"},
                 "path_algorithmic_gbs": round(path_bytes(b, c, h, w) / (ms_step * 1e-3) / 1e9, 1)}
         kernels = None
         if breakdown is not None:

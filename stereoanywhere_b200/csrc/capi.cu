@@ -27,6 +27,19 @@ int num_sms() {
   return cached;
 }
 
+long long l2_bytes() {
+  static thread_local int cached_dev = -1;
+  static thread_local long long cached = 126ll << 20;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return cached;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrL2CacheSize, dev) == cudaSuccess && n > 0) cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
 }  // namespace sa
 
 extern "C" int sa_abi_version(void) { return SA_ABI_VERSION; }

@@ -214,6 +214,7 @@ struct PLookupArgs {
   const float* nr;
   int H, Wimg;
   float divisor, inv_divisor, post_scale;
+  int out_evict_first;  // TMA output stores carry the L2 evict_first hint (set by the launcher, see launch_packed_tt)
   // factored mono volume (FV >= 0): packed[FV] holds the packed pyramid of the RIGHT NORMAL MAP's rows,
   // [(b*3 + c)*H + h][nblk][32]; nl / H / Wimg / divisor / inv_divisor / post_scale as above
 };
@@ -567,8 +568,12 @@ __global__ void __maxnreg__(OTF >= 0 ? 128 : (TMA ? SA_LOOKUP_REGS_TMA : SA_LOOK
     if (tid < NV) {
       // evict_first: the 69 MB a launch writes would otherwise sit dirty in the L2 and push out the packed lines and
       // right-normal rows that the next iteration reads again (coordinates move by a fraction of a pixel per
-      // iteration) - 22.7 -> 21.1 us per dual lookup at KITTI size (profiles/r2/lookup_l2_policy_sweep.txt)
-      tma_store_3d_hint(tid ? &map_o1 : &map_o0, buf + tid * NC * SP, (int)hw0, 0, (int)b, l2_evict_first_policy());
+      // iteration) - 22.7 -> 21.1 us per dual lookup at KITTI size (profiles/r2/lookup_l2_policy_sweep.txt).  Only
+      // while the output of a launch fits the L2 with room to spare: beyond that the hint costs 1-2 %.
+      if (a.out_evict_first)
+        tma_store_3d_hint(tid ? &map_o1 : &map_o0, buf + tid * NC * SP, (int)hw0, 0, (int)b, l2_evict_first_policy());
+      else
+        tma_store_3d(tid ? &map_o1 : &map_o0, buf + tid * NC * SP, (int)hw0, 0, (int)b);
       tma_commit();
       tma_wait_read<0>();   // the tile must outlive the store's read of it
     }
@@ -654,6 +659,8 @@ static int launch_packed_tt(PLookupArgs a, int B, cudaStream_t st) {
     }
   }
   dim3 grid((a.HW + TILE - 1) / TILE, B);
+  // output bytes of this launch against the L2: the hint pays up to ~0.6 of the cache (KITTI batch 8: 69 MB of 126)
+  a.out_evict_first = (long long)NV * NC * 4 * a.HW * B * 10 <= l2_bytes() * 6;
   kern<<<grid, NV * TILE, smem, st>>>(a, m0, m1);
   return finish_launch("sa_lookup_packed");
 }

@@ -318,3 +318,20 @@ def test_full_size_results_repeat_bit_for_bit(sa):
         assert torch.equal(hs, h0) and torch.equal(hm, hm0)
         cs, cm = sa.lookup_pair_convc1(first, mono, coords, wgt, bias)
         assert torch.equal(cs, c0) and torch.equal(cm, cm0)
+
+
+def test_lookup_store_policy_does_not_change_results(sa):
+    """The dual lookup's TMA output stores carry an L2 evict_first hint only while a launch's output is below ~0.6 of the
+    L2 (csrc/packed.cu, launch_packed_tt).  Ten KITTI-size pairs are above that bound, slices of five pairs below it:
+    same bits either way."""
+    B = sa.CorrBlockB200
+    b, c, h, w = 10, 32, 96, 312
+    fl, fr, nl, nr, coords, disp, conf = _inputs(b, c, h, w, w, seed=11)
+    assert 2 * 36 * 4 * h * w * b * 10 > torch.cuda.get_device_properties(0).L2_cache_size * 6   # the no-hint branch
+    s, m = B.lookup_pair(B.from_features(fl, fr, truncate=(disp, conf, 0.9)), B.from_normals(nl, nr), coords)
+    for lo, hi in ((0, 5), (5, 10)):
+        sl = slice(lo, hi)
+        assert 2 * 36 * 4 * h * w * (hi - lo) * 10 <= torch.cuda.get_device_properties(0).L2_cache_size * 6
+        s2, m2 = B.lookup_pair(B.from_features(fl[sl], fr[sl], truncate=(disp[sl], conf[sl], 0.9)), B.from_normals(nl[sl], nr[sl]),
+                               coords[sl].contiguous())
+        assert torch.equal(s[sl], s2) and torch.equal(m[sl], m2)

@@ -32,6 +32,7 @@ struct LcArgs {
   const float* bias;    // [64]
   long long coords_bstride;
   int HW, nblk, B;
+  int reverse;  // walk the tiles backwards (alternate launches on the same volume: csrc/packed.cu, next_direction)
   // FACT: packed[1] is the packed pyramid of the right normal map's rows ([(b*3 + c)*H + h][nblk][32], see
   // csrc/packed.cu, factored mono volume), nl the left normals [B,3,H,Wimg], kscale = post_scale / divisor
   const float* nl;
@@ -115,7 +116,8 @@ __global__ void __launch_bounds__(2 * kLcTile, 4) lookup_conv_kernel(const LcArg
   const int tiles_x = (a.HW + TILE - 1) / TILE;
   const long long ntiles = (long long)tiles_x * a.B;
   uint32_t phase = 0;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (long long it = blockIdx.x; it < ntiles; it += gridDim.x) {
+    const long long tile = a.reverse ? ntiles - 1 - it : it;
     const unsigned b = (unsigned)(tile / tiles_x);
     const unsigned hw0 = (unsigned)(tile - (long long)b * tiles_x) * TILE;
   const int npx = min(TILE, a.HW - (int)hw0);
@@ -337,8 +339,11 @@ __global__ void __launch_bounds__(2 * kLcTile, 4) lookup_conv_kernel(const LcArg
 }  // namespace sa
 
 namespace sa {
+int lookup_next_direction(const void* key);  // csrc/packed.cu
+
 template <bool FACT>
-static int launch_lookup_conv(const LcArgs& a, cudaStream_t st, const char* what) {
+static int launch_lookup_conv(LcArgs a, cudaStream_t st, const char* what) {
+  a.reverse = lookup_next_direction(a.packed[0]);
   const size_t smem = 1024 + 2 * kLcABytes + kLcBBytes + (kLcN + 2 * kLcTile) * sizeof(float) + 32;
   cudaError_t e = cudaFuncSetAttribute(lookup_conv_kernel<FACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) SA_FAIL((int)e, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));

@@ -215,6 +215,7 @@ struct PLookupArgs {
   int H, Wimg;
   float divisor, inv_divisor, post_scale;
   int out_evict_first;  // TMA output stores carry the L2 evict_first hint (set by the launcher, see launch_packed_tt)
+  int reverse;          // walk the pixel tiles backwards (alternate launches, see next_direction)
   // factored mono volume (FV >= 0): packed[FV] holds the packed pyramid of the RIGHT NORMAL MAP's rows,
   // [(b*3 + c)*H + h][nblk][32]; nl / H / Wimg / divisor / inv_divisor / post_scale as above
 };
@@ -380,8 +381,8 @@ __global__ void __maxnreg__(OTF >= 0 ? 128 : (TMA ? SA_LOOKUP_REGS_TMA : SA_LOOK
   float4* s_n = reinterpret_cast<float4*>(s_x + 2 * TILE);
 
   const int tid = threadIdx.x;
-  const unsigned b = blockIdx.y;
-  const unsigned hw0 = blockIdx.x * TILE;
+  const unsigned b = a.reverse ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const unsigned hw0 = (a.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * TILE;
   const int npx = min(TILE, a.HW - (int)hw0);
 
   if (tid < TILE) {
@@ -637,6 +638,29 @@ static int output_map(CUtensorMap* m, const float* out, int B, int HW, int tile)
   return 0;
 }
 
+// Consecutive lookups of one volume walk its pixel tiles in OPPOSITE directions.  The GRU's coordinates move by a
+// fraction of a pixel per iteration, so a launch re-reads mostly the lines (and right-normal rows) the previous one
+// read; walking forwards every time, the lines a launch needs first are the ones the previous launch read longest
+// ago - the first to have left the L2 (the cyclic-scan worst case of an LRU-like cache).  Walking back and forth, a
+// launch starts where its predecessor stopped: 21.2 -> 19.9 us per dual lookup at KITTI size (two packed volumes:
+// 23.3 -> 21.7).  Results do not depend on the direction.  Parity per volume (keyed by its packed array) and per
+// thread; under CUDA-graph capture every captured launch keeps the direction it was captured with.
+// SA_B200_LOOKUP_ALTERNATE=0 walks forwards always.
+static int next_direction(const void* key) {
+  static const bool on = !(getenv("SA_B200_LOOKUP_ALTERNATE") && atoi(getenv("SA_B200_LOOKUP_ALTERNATE")) == 0);
+  if (!on) return 0;
+  struct Entry { const void* p; unsigned n; };
+  static thread_local Entry tab[8];
+  static thread_local int next = 0;
+  for (int i = 0; i < 8; ++i)
+    if (tab[i].p == key) return (int)(tab[i].n++ & 1u);
+  tab[next] = Entry{key, 1u};
+  next = (next + 1) & 7;
+  return 0;
+}
+
+int lookup_next_direction(const void* key) { return next_direction(key); }  // for csrc/lookup_conv.cu
+
 template <int NV, int TILE, int OTF, int FV, bool TMA, int H0>
 static int launch_packed_tt(PLookupArgs a, int B, cudaStream_t st) {
   constexpr int NC = 36, SP = TMA ? TILE : TILE + 4;
@@ -661,18 +685,23 @@ static int launch_packed_tt(PLookupArgs a, int B, cudaStream_t st) {
   dim3 grid((a.HW + TILE - 1) / TILE, B);
   // output bytes of this launch against the L2: the hint pays up to ~0.6 of the cache (KITTI batch 8: 69 MB of 126)
   a.out_evict_first = (long long)NV * NC * 4 * a.HW * B * 10 <= l2_bytes() * 6;
+  {
+    static const int env = getenv("SA_B200_LOOKUP_EVICT") ? atoi(getenv("SA_B200_LOOKUP_EVICT")) : -1;
+    if (env >= 0) a.out_evict_first = env;
+  }
+  a.reverse = next_direction(a.packed[0] ? a.packed[0] : a.packed[1]);
   kern<<<grid, NV * TILE, smem, st>>>(a, m0, m1);
   return finish_launch("sa_lookup_packed");
 }
 
-// Output path.  Factored mono form: one TMA tensor store per volume (22.9 us per dual lookup at KITTI size against
-// 23.8 with the transposed 128-bit stores - it is bound by L1 / shared-memory wavefronts).  Two packed volumes: the
-// 128-bit stores (23.2 against 24.4 us with TMA stores - that form is DRAM-bound and its streaming `no_allocate`
-// stores disturb the line reads less).  SA_B200_LOOKUP_TMA=0/1 overrides.
+// Output path.  Dual lookups: one TMA tensor store per volume with the L2 evict_first hint (factored mono form 20.0 us
+// per dual lookup at KITTI size against 21.3 with the transposed 128-bit stores; two packed volumes 21.45 against
+// 21.75 - before the hint and the alternating direction the TMA stores lost there, 24.4 against 23.2).  Single
+// lookups keep the 128-bit stores (12.3 against 12.6 us).  SA_B200_LOOKUP_TMA=0/1 overrides.
 template <int NV, int TILE, int OTF, int FV, int H0>
 static int launch_packed_t(const PLookupArgs& a, int B, cudaStream_t st) {
   static const int env = getenv("SA_B200_LOOKUP_TMA") ? atoi(getenv("SA_B200_LOOKUP_TMA")) : -1;
-  const bool want = env >= 0 ? env != 0 : (FV >= 0);
+  const bool want = env >= 0 ? env != 0 : (FV >= 0 || (NV == 2 && OTF < 0));
   if (want && (a.HW & 3) == 0 && encode_fn() != nullptr) return launch_packed_tt<NV, TILE, OTF, FV, true, H0>(a, B, st);
   return launch_packed_tt<NV, TILE, OTF, FV, false, H0>(a, B, st);
 }

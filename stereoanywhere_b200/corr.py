@@ -228,7 +228,7 @@ class CorrBlockB200:
     #: left normal while staging: no mono pack pass (241 us) and half the lookup's DRAM reads; within fp32 rounding
     #: (<= 1e-6 abs) of the packed mode.  "packed" writes the packed pyramid of the volume itself, bit-identical to
     #: `cls(cls.mono_corr(nL, nR))`.  "otf" keeps only the normal maps and forms 80 level-0 values per pixel inside
-    #: the lookup kernel - bit-identical to "packed" too, but 48 us instead of 23 us per dual lookup (a memory-saving mode).
+    #: the lookup kernel - bit-identical to "packed" too, but 47 us instead of 20 us per dual lookup (a memory-saving mode).
     #: SA_B200_MONO overrides the default.
     mono_mode = os.environ.get("SA_B200_MONO", "factored")
 
